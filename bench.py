@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- faces/sec of the RetinaFace mnet25 detect path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = one pass of the hot path (u8 images -> conv0..SSH -> fused heads+decode -> NMS)
+over one batch of synthetic S-real input (the golden photo letter-boxed to the
+network size, element i rolled by 8*i pixels so every image has faces but distinct content).
+
+Printed JSON (rank 0, one line):
+  value      faces/s, device-timed: inputs already resident in HBM (a ring of batches larger than
+             2x L2 so that no step finds its input in L2), CUDA events on the library's stream,
+             max over ranks, whole job (all GPUs).
+  e2e        the same metric through the public C-ABI call rf_detect_batch with HOST (pinned)
+             images: H2D + compute + D2H of the faces inside the timed region, every step.
+  roofline   dominant kernel: algorithmic bytes (layer-granular) / CUDA-event time of
+             that kernel launched K times on the library's stream, vs MEASURED_PEAKS.json.
+  cpu_baseline  the oracle (cv2.dnn FP32 forward of the same caffemodel through a generated prototxt +
+             oracle/postproc.c) timed on the host cores on a bounded sample (rank 0, N=1 only).
+
+--impl reference runs only that CPU arm (the reference's own CPU path cannot be built here:
+BVLC Caffe / OpenCV C++ / TensorRT are absent -- DESIGN.md), on the same config/metric/unit.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "mnet25_fp16_b8_448": dict(model="mnet25", precision="fp16", batch=8, h=448, w=448),
+    "mnet25_fp32_b8_448": dict(model="mnet25", precision="fp32", batch=8, h=448, w=448),
+    "mnet25_fp16_b1_448": dict(model="mnet25", precision="fp16", batch=1, h=448, w=448),
+    "mnet25_fp16_b32_448": dict(model="mnet25", precision="fp16", batch=32, h=448, w=448),
+    # configs[3]: large input / many-anchor NMS stress
+    "mnet25_fp16_b8_1280x896": dict(model="mnet25", precision="fp16", batch=8, h=896, w=1280),
+}
+DEFAULT_WORKLOAD = "mnet25_fp16_b8_448"
+SCORE_THR, NMS_THR = 0.9, 0.4  # main.cpp:43, RetinaFace.h:66
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], src="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, src="fallback")
+
+
+def make_batches(wl, count, rank):
+    """`count` distinct S-real batches (u8 [count][B][H][W][3])."""
+    import cv2
+    from oracle.inputs import letterbox_bgr_u8
+    img = cv2.imread(os.path.join(GOLD, "data", "img.jpg"))
+    base = letterbox_bgr_u8(img, wl["h"], wl["w"])
+    out = np.empty((count, wl["batch"], wl["h"], wl["w"], 3), dtype=np.uint8)
+    for s in range(count):
+        for i in range(wl["batch"]):
+            out[s, i] = np.roll(base, 8 * (i + wl["batch"] * (s + count * rank)), axis=1)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons, sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_ev = gpu, [], threading.Event()
+
+    def run(self):
+        while not self.stop_ev.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.1)
+
+    def summary(self):
+        self.stop_ev.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle; the reference's own CPU-Caffe path is unbuildable here)
+# ------------------------------------------------------------------------------------------------
+class CpuPath:
+    def __init__(self, wl, threads):
+        import cv2
+        import tempfile
+        from oracle import topology
+        from oracle.postproc import PostprocOracle
+        cv2.setNumThreads(threads)
+        self.cv2, self.topology, self.wl = cv2, topology, wl
+        d = tempfile.mkdtemp()
+        p = os.path.join(d, "oracle.prototxt")
+        open(p, "w").write(topology.to_prototxt(wl["h"], wl["w"], wl["batch"]))
+        self.net = cv2.dnn.readNetFromCaffe(p, os.path.join(GOLD, "weights", wl["model"] + ".caffemodel"))
+        self.post = PostprocOracle()
+        self.threads = threads
+
+    def step(self, batch_u8):
+        """RetinaFace::detect on the CPU: u8->f32 RGB planar, forward, decode+NMS.  Returns #faces."""
+        x = np.ascontiguousarray(batch_u8[..., ::-1].transpose(0, 3, 1, 2), dtype=np.float32)
+        self.net.setInput(x)
+        outs = self.net.forward(self.topology.OUTPUT_BLOBS)
+        faces = 0
+        for i in range(batch_u8.shape[0]):
+            r = self.post.postprocess([o[i] for o in outs], self.wl["h"], self.wl["w"], SCORE_THR, NMS_THR)
+            faces += len(r["faces"])
+        return faces
+
+
+def cpu_measure(wl, batches, budget_s, min_steps=2):
+    threads = os.cpu_count() or 1
+    cpu = CpuPath(wl, threads)
+    cpu.step(batches[0])  # warm-up
+    t0 = time.perf_counter()
+    faces = steps = 0
+    while (time.perf_counter() - t0 < budget_s or steps < min_steps) and steps < 10_000:
+        faces += cpu.step(batches[steps % len(batches)])
+        steps += 1
+    dt = time.perf_counter() - t0
+    return dict(value=faces / dt, unit="faces/s", cores=threads, kind="port",
+                sample=f"{steps} batches of {wl['batch']} images ({steps * wl['batch']} images, {dt:.1f} s): cv2.dnn FP32 forward "
+                       f"of {wl['model']}.caffemodel + oracle/postproc.c decode/NMS, {threads} threads",
+                images_per_s=steps * wl["batch"] / dt), dt, steps
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 3)
+    config = dict(workload=args.workload, model=wl["model"] + ".caffemodel (reference weights)", precision=wl["precision"],
+                  batch_per_gpu=wl["batch"], global_batch=wl["batch"] * world, input=f"{wl['w']}x{wl['h']}",
+                  score_thr=SCORE_THR, nms_thr=NMS_THR, parallelism=f"dp{world}", input_data="S-real: golden photo letter-boxed, rolled 8*i px")
+
+    if args.impl == "reference":
+        # the reference arm: CPU path, rank 0 only
+        if rank != 0:
+            return
+        sample = make_batches(wl, 4, 0)
+        cpu = CpuPath(wl, os.cpu_count() or 1)
+        for _ in range(min(W, 3)):
+            cpu.step(sample[0])
+        # each step = one batch; bound the run to a few minutes
+        t0 = time.perf_counter()
+        faces = 0
+        steps = 0
+        for s in range(K):
+            faces += cpu.step(sample[s % len(sample)])
+            steps += 1
+            if time.perf_counter() - t0 > 150:
+                break
+        dt = time.perf_counter() - t0
+        v = faces / dt
+        line = dict(metric="faces/sec (end-to-end detect)", value=v, unit="faces/s", n_gpus=args.gpus, steps=steps, warmup=W,
+                    ms_per_step=dt / steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic", impl="reference", config=config, images_per_s=steps * wl["batch"] / dt,
+                    cpu_baseline=dict(value=v, unit="faces/s", cores=cpu.threads, kind="port",
+                                      sample=f"{steps} steps x {wl['batch']} images: cv2.dnn FP32 forward + oracle/postproc.c "
+                                             "(the reference's CPU-Caffe path cannot be built: Caffe/OpenCV C++ absent)"),
+                    e2e=dict(value=v, unit="faces/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from retinaface_b200 import RF_PREC_FP16, RF_PREC_FP32, Engine
+    prec = RF_PREC_FP16 if wl["precision"] == "fp16" else RF_PREC_FP32
+    B, H, Wd = wl["batch"], wl["h"], wl["w"]
+    eng = Engine(os.path.join(GOLD, "weights", wl["model"] + ".caffemodel"), H, Wd, precision=prec, max_batch=B,
+                 max_faces=128, device=local)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=local)
+    img_bytes = B * H * Wd * 3
+    l2_bytes = 126 * 2**20
+    ring = max(4, min(256, -(-2 * l2_bytes // img_bytes)))     # input ring > 2 x L2
+    host = make_batches(wl, ring, rank)
+    pinned = torch.from_numpy(host).pin_memory()
+    dev = pinned.to(f"cuda:{local}", non_blocking=False)       # device-resident inputs for `value`
+    faces = np.empty((B, eng.max_faces, 15), dtype=np.float32)
+    counts = np.zeros(B, dtype=np.int32)
+    pin_np = pinned.numpy()
+
+    def e2e_step(slot):
+        imgs = [pin_np[slot, i] for i in range(B)]
+        return eng.detect_batch(imgs, SCORE_THR, NMS_THR)
+
+    # faces per ring slot (deterministic; also the warm-up of both paths)
+    faces_per_slot = np.zeros(ring, dtype=np.int64)
+    for s in range(ring):
+        faces_per_slot[s] = sum(len(f) for f in e2e_step(s))
+    # all-gather buffer for N>1: the fixed-size per-image detection records
+    det_view = cnt_view = gathered = gathered_c = None
+
+    def dev_tensor(ptr, nbytes):
+        class _W:  # minimal __cuda_array_interface__ carrier
+            pass
+        w = _W()
+        w.__cuda_array_interface__ = dict(shape=(nbytes,), typestr="|u1", data=(ptr, False), version=2)
+        return torch.as_tensor(w, device=f"cuda:{local}")
+
+    dptr, cptr = eng.detect_device(B, SCORE_THR, NMS_THR, dev[0].data_ptr())
+    eng.synchronize()
+    if world > 1:
+        det_view = dev_tensor(dptr, B * eng.max_faces * 64)
+        cnt_view = dev_tensor(cptr, B * 4)
+        gathered = torch.empty(world * det_view.numel(), dtype=torch.uint8, device=f"cuda:{local}")
+        gathered_c = torch.empty(world * cnt_view.numel(), dtype=torch.uint8, device=f"cuda:{local}")
+
+    def device_step(slot):
+        eng.detect_device(B, SCORE_THR, NMS_THR, dev[slot].data_ptr())
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, det_view)
+                dist.all_gather_into_tensor(gathered_c, cnt_view)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed value ---------------------------------------------------------------
+    for i in range(W):
+        device_step(i % ring)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for i in range(K):
+        device_step((W + i) % ring)
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    dev_faces = int(sum(faces_per_slot[(W + i) % ring] for i in range(K)))
+
+    # ---- end-to-end through rf_detect_batch (host pinned in, host faces out) ------------------
+    for i in range(W):
+        e2e_step(i % ring)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_faces = 0
+    for i in range(K):
+        out = e2e_step((W + i) % ring)
+        e2e_faces += sum(len(f) for f in out)
+        if world > 1:
+            pass  # the all-gathered records live on the device path; host results are per rank
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.summary()
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s, float(dev_faces), float(e2e_faces)], dtype=torch.float64, device=f"cuda:{local}")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s = float(tmax[0]), float(tmax[1])
+        dev_faces, e2e_faces = int(tsum[2]), int(tsum[3])
+
+    line = None
+    if rank == 0:
+        pk = peaks()
+        value = dev_faces / (dev_ms * 1e-3)
+        # ---- roofline of the dominant kernel (direct launches, CUDA events on the library stream) ----
+        prof = eng.profile_layers(B, iters=max(10, min(K, 100)))
+        tot = sum(p["ms"] for p in prof)
+        top = max(prof, key=lambda p: p["ms"])
+        ach_gbs = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+        ach_tf = top["flops"] / (top["ms"] * 1e-3) / 1e12
+        roof = dict(bound="hbm", kernel=top["name"], achieved=ach_gbs, peak=pk["hbm_gbs"], unit="GB/s", frac=ach_gbs / pk["hbm_gbs"],
+                    traffic=None, peak_source=pk["src"], kernel_ms=top["ms"], kernel_share_of_step=top["ms"] / tot,
+                    tensor_tflops=ach_tf, tensor_frac=ach_tf / pk["bf16_tflops"],
+                    step_algorithmic_gb=sum(p["bytes"] for p in prof) / 1e9, step_algorithmic_gflop=sum(p["flops"] for p in prof) / 1e9,
+                    step_sum_of_kernels_ms=tot)
+        line = dict(metric="faces/sec (end-to-end detect)", value=value, unit="faces/s", n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=dev_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f16" if prec == RF_PREC_FP16 else "f32", data="synthetic", config=dict(config, l2_policy=f"input ring of {ring} batches = {ring * img_bytes / 2**20:.0f} MiB > 2x L2; activations reused in place"),
+                    images_per_s=K * B * world / (dev_ms * 1e-3), clocks=clocks,
+                    e2e=dict(value=e2e_faces / e2e_s, unit="faces/s", h2d_bytes_per_step=img_bytes,
+                             d2h_bytes_per_step=B * 4 + B * eng.max_faces * 64, images_per_s=K * B * world / e2e_s,
+                             ms_per_step=e2e_s / K * 1e3, timing="host wall clock around K blocking rf_detect_batch calls"),
+                    gpu_launches=K * eng.launches_per_batch(B), launches_per_step=eng.launches_per_batch(B), roofline=roof,
+                    layers=[dict(name=p["name"], us=round(p["ms"] * 1e3, 2)) for p in prof])
+    eng_close = eng.close
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb, _, _ = cpu_measure(wl, host[:4], args.cpu_seconds)
+        line["cpu_baseline"] = cb
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    eng_close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,162 @@
+/*
+ * rf_b200.h -- C ABI of librf_b200.so: the B200-native (sm_100a) RetinaFace mnet25 detect path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer of its own: its seam is the
+ * C++ class `TrtRetinaFaceNet` plus three free CUDA launchers used by `RetinaFace`
+ * (retinaface/RetinaFace.cpp:4-6,275-291,584-608,655,670-684).  Each entry point below names
+ * the reference interface it replaces.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns RF_OK (0) or a negative rf_status; rf_last_error() gives text.
+ *     Nothing aborts/exits (the reference abort()s/exit()s/throws: trtutility.h:9-16,
+ *     trtnetbase.cpp:201-204, RetinaFace.cpp:327-335).
+ *   - one handle = one device + one stream; calls on a handle are serialised by the caller
+ *     (the reference is single-threaded and non re-entrant).
+ *   - there is NO CPU fallback: every compute entry point runs CUDA kernels on the handle's
+ *     device and fails with RF_ERR_CUDA if that is impossible.
+ *   - images are u8 BGR HWC like cv::Mat (RetinaFace.cpp:594), results are FaceDetectInfo
+ *     records (RetinaFace.h:37-42) in network-input pixel coordinates (RetinaFace.cpp:707).
+ */
+#ifndef RF_B200_H
+#define RF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RF_B200_ABI_VERSION 1
+
+typedef enum rf_status {
+    RF_OK = 0,
+    RF_ERR_INVALID_ARG = -1,
+    RF_ERR_IO = -2,          /* model file missing / unreadable */
+    RF_ERR_MODEL = -3,       /* caffemodel does not hold the mnet25 topology */
+    RF_ERR_CUDA = -4,        /* CUDA runtime / launch failure (text in rf_last_error) */
+    RF_ERR_NO_DEVICE = -5,   /* no sm_100 device: the library has no CPU path */
+    RF_ERR_CAPACITY = -6,    /* batch / image larger than the handle was created for */
+    RF_ERR_UNSUPPORTED = -7
+} rf_status;
+
+/* Arithmetic of the network body.  Head 1x1 convs, softmax, decode and NMS are always FP32. */
+typedef enum rf_precision {
+    RF_PREC_FP32 = 0,   /* FP32 storage + FP32 SIMT math: the tight-parity mode */
+    RF_PREC_FP16 = 1,   /* FP16 NHWC activations/weights, FP32 accumulate (tcgen05 where GEMM-shaped) */
+    RF_PREC_INT8 = 2    /* INT8 activations with the TensorRT calibration-table scales */
+} rf_precision;
+
+/* == FaceDetectInfo (RetinaFace.h:37-42): score, rect(x1,y1,x2,y2), pts.x[5], pts.y[5]. */
+typedef struct rf_face {
+    float score;
+    float x1, y1, x2, y2;
+    float lx[5];
+    float ly[5];
+} rf_face;
+
+/* Device/all-gather record: rf_face + the anchor's emission index (stride 32->16->8, anchor,
+ * row-major position: the order of the reference's decode loop, RetinaFace.cpp:666-690).
+ * 64 bytes. */
+typedef struct rf_det {
+    rf_face face;
+    int32_t anchor_index;
+} rf_det;
+
+typedef struct rf_config {
+    const char *caffemodel_path;   /* replaces buildTrtContext(prototxt, caffemodel), RetinaFace.cpp:276 */
+    const char *int8_table_path;   /* TensorRT EntropyCalibration2 cache (trtnetbase.cpp:13) or NULL */
+    int precision;                 /* rf_precision */
+    int net_w, net_h;              /* network input size (prototxt line 7 in the reference); multiples of 32 */
+    int max_batch;                 /* reference: maxBatchSize = 8 (trtretinafacenet.cpp:21) */
+    int max_faces;                 /* per-image output capacity (faces kept after NMS); 0 -> 256 */
+    int device;                    /* CUDA device ordinal */
+    int max_image_w, max_image_h;  /* largest caller image (reference: 4096x3072, RetinaFace.cpp:325); 0 -> net size */
+    unsigned flags;                /* RF_FLAG_* */
+} rf_config;
+
+#define RF_FLAG_NO_GRAPH      0x1u  /* launch kernels directly instead of replaying a CUDA graph */
+#define RF_FLAG_NO_TENSORCORE 0x2u  /* FP16: use the SIMT kernels for GEMM-shaped layers too */
+
+typedef struct rf_handle_s *rf_handle;
+
+/* Process-wide info, callable without a GPU. */
+int rf_abi_version(void);
+const char *rf_build_info(void);            /* arch flags etc. */
+const char *rf_status_string(int status);
+
+/* Replaces RetinaFace::RetinaFace's engine setup (RetinaFace.cpp:274-302): parses the
+ * caffemodel, folds BatchNorm+Scale(+bias) in FP32, repacks weights, allocates device and
+ * pinned memory, builds CUDA graphs lazily.  On failure *out = NULL and the message is
+ * available from rf_last_error(NULL). */
+int rf_create(const rf_config *cfg, rf_handle *out);
+void rf_destroy(rf_handle h);
+const char *rf_last_error(rf_handle h);     /* h may be NULL: last rf_create error */
+
+/* Library-owned pinned staging for network-sized inputs: max_batch * net_h * net_w * 3 bytes.
+ * Writing images here lets rf_detect_batch skip its host-side staging copy. */
+uint8_t *rf_pinned_input(rf_handle h);
+/* Library-owned DEVICE input buffer of the same shape: a caller that already has its images on
+ * the GPU writes them here and passes this pointer to rf_detect_batch_device (no D2D copy). */
+uint8_t *rf_device_input(rf_handle h);
+
+/* Replaces RetinaFace::detect / detectBatchImages (RetinaFace.cpp:576-747, 749-940), end to
+ * end: host u8 BGR HWC images (any size <= max_image; letter-boxed top-left into the network
+ * size, never up-scaled) -> H2D -> network -> decode + threshold + NMS on the GPU -> D2H.
+ * `row_strides` in bytes (NULL = packed).  Writes up to max_faces faces per image to
+ * out_faces[i * max_faces ...] in descending score order and the count to out_counts[i].
+ * out_anchor_index (optional, same layout) receives each face's anchor emission index.
+ * Blocking: returns when the results are in the caller's arrays. */
+int rf_detect_batch(rf_handle h, const uint8_t *const *bgr_images, const int *widths, const int *heights,
+                    const int *row_strides, int n, float score_threshold, float nms_threshold,
+                    rf_face *out_faces, int *out_counts, int32_t *out_anchor_index);
+
+/* Device-resident variant: `dev_bgr` holds n network-sized u8 BGR HWC images (contiguous) in
+ * device memory; results stay on the device: *dev_dets -> [max_batch][max_faces] rf_det,
+ * *dev_counts -> [max_batch] int32 (kept count, clamped to max_faces).  Asynchronous on the
+ * handle's stream (see rf_stream / rf_synchronize).  This is the buffer a multi-GPU caller
+ * all-gathers. */
+int rf_detect_batch_device(rf_handle h, const uint8_t *dev_bgr, int n, float score_threshold,
+                           float nms_threshold, const rf_det **dev_dets, const int32_t **dev_counts);
+
+/* Parity/debug: replaces TrtRetinaFaceNet::doInference + blob_by_name (trtretinafacenet.cpp:48-114).
+ * Host network-sized images in, the 9 head blobs out in the reference's blob order
+ * (trtretinafacenet.cpp:23-31), NCHW float32, each heads_out[k] sized n*C*h*w. */
+int rf_forward_heads(rf_handle h, const uint8_t *bgr_net_sized, int n, float *const heads_out[9]);
+
+/* Kernel-level parity: replaces the host decode loop + nms (RetinaFace.cpp:661-726, 439-492)
+ * on caller-supplied head blobs (host, layout as rf_forward_heads).  Same outputs as
+ * rf_detect_batch plus the pre-NMS candidate count per image (optional). */
+int rf_postprocess(rf_handle h, const float *const heads[9], int n, float score_threshold,
+                   float nms_threshold, rf_face *out_faces, int *out_counts, int32_t *out_anchor_index,
+                   int *out_num_candidates);
+
+/* Preprocess parity: replaces imageROIResize8U3C + the OpenCV branch (RetinaFace.cpp:593-647):
+ * letter-boxes one host image into a host net_h*net_w*3 u8 BGR buffer using the GPU kernel. */
+int rf_preprocess(rf_handle h, const uint8_t *bgr, int width, int height, int row_stride, uint8_t *out_net_sized);
+
+/* Introspection. */
+int rf_get_net_size(rf_handle h, int *net_w, int *net_h, int *max_batch, int *max_faces);
+int rf_num_anchors(rf_handle h);            /* per image: 8,232 @448x448, 47,040 @1280x896 */
+void *rf_stream(rf_handle h);               /* cudaStream_t */
+int rf_synchronize(rf_handle h);
+/* Number of kernel launches (graph kernel nodes) one rf_detect_batch_device of batch n issues. */
+int rf_launches_per_batch(rf_handle h, int n);
+/* Names + device times (ms, CUDA events, direct launches) of each kernel of one forward of
+ * batch n: fills up to cap entries, returns the count.  For bench.py's roofline line. */
+int rf_profile_layers(rf_handle h, int n, int iters, char (*names)[64], float *ms, double *bytes, double *flops, int cap);
+
+/* Debug / parity aids (not part of the drop-in surface): fetch a materialised activation by its
+ * Caffe top name (e.g. "mobilenet0_relu10_fwd", "_plus0", "rf_c1_det_concat_relu") as NCHW
+ * float32 after a forward; rf_debug_keep_all disables activation-buffer reuse so every tensor
+ * of the last forward survives. */
+int rf_debug_get_tensor(rf_handle h, const char *name, int n, float *out_nchw, int *c, int *hh, int *ww);
+int rf_debug_keep_all(rf_handle h);
+/* Host-only (works without a GPU): the folded FP32 weights / bias of one convolution layer as the
+ * engine holds them; dims = {cout, cin/groups, k, k}.  For CPU-side tests of the model front end. */
+int rf_model_inspect(const char *caffemodel_path, const char *layer, float *w, int wcap, float *b, int bcap, int dims[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RF_B200_H */

@@ -164,7 +164,7 @@ def synth_heads(net_h: int, net_w: int, n_cand: int, seed: int = 1, n_centres: i
     face[chosen] = True
     # unique scores: candidates in (thr, 1), the rest in (0, thr)
     hi = thr + (1 - thr) * (rng.permutation(n_cand) + 0.5) / n_cand
-    lo = rng.uniform(0.0, thr * 0.98, size=total)
+    lo = thr * 0.98 * (rng.permutation(total) + 0.5) / total   # unique as float32 too
     score = lo.astype(np.float32)
     score[chosen] = hi.astype(np.float32)
     off = 0

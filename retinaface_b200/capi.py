@@ -1,0 +1,257 @@
+"""ctypes binding of include/rf_b200.h.  Fails loudly when librf_b200.so is missing: there is no
+Python / CPU implementation of the path behind it."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+RF_PREC_FP32, RF_PREC_FP16, RF_PREC_INT8 = 0, 1, 2
+RF_FLAG_NO_GRAPH, RF_FLAG_NO_TENSORCORE = 0x1, 0x2
+FACE_FLOATS = 15
+
+# every symbol include/rf_b200.h declares (checked by tests/test_capi_symbols.py)
+EXPORTS = [
+    "rf_abi_version", "rf_build_info", "rf_status_string", "rf_create", "rf_destroy", "rf_last_error",
+    "rf_pinned_input", "rf_device_input", "rf_detect_batch", "rf_detect_batch_device", "rf_forward_heads",
+    "rf_postprocess", "rf_preprocess", "rf_get_net_size", "rf_num_anchors", "rf_stream", "rf_synchronize",
+    "rf_launches_per_batch", "rf_profile_layers", "rf_debug_get_tensor", "rf_debug_keep_all", "rf_model_inspect",
+]
+
+
+class RfError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"librf_b200 status {status}: {msg}")
+        self.status = status
+
+
+class _Config(C.Structure):
+    _fields_ = [("caffemodel_path", C.c_char_p), ("int8_table_path", C.c_char_p), ("precision", C.c_int),
+                ("net_w", C.c_int), ("net_h", C.c_int), ("max_batch", C.c_int), ("max_faces", C.c_int),
+                ("device", C.c_int), ("max_image_w", C.c_int), ("max_image_h", C.c_int), ("flags", C.c_uint)]
+
+
+def lib_path() -> str:
+    return os.environ.get("RF_B200_LIB", os.path.join(_HERE, "librf_b200.so"))
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen librf_b200.so (built in-tree by retinaface_b200/build.py or __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError(f"{p} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(retinaface_b200 has no CPU fallback)")
+    lib = C.CDLL(p)
+    lib.rf_build_info.restype = C.c_char_p
+    lib.rf_status_string.restype = C.c_char_p
+    lib.rf_last_error.restype = C.c_char_p
+    lib.rf_last_error.argtypes = [C.c_void_p]
+    lib.rf_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+    lib.rf_destroy.argtypes = [C.c_void_p]
+    lib.rf_destroy.restype = None
+    lib.rf_pinned_input.restype = C.c_void_p
+    lib.rf_pinned_input.argtypes = [C.c_void_p]
+    lib.rf_device_input.restype = C.c_void_p
+    lib.rf_device_input.argtypes = [C.c_void_p]
+    lib.rf_stream.restype = C.c_void_p
+    lib.rf_stream.argtypes = [C.c_void_p]
+    for name in ("rf_synchronize", "rf_num_anchors"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.rf_launches_per_batch.argtypes = [C.c_void_p, C.c_int]
+    lib.rf_get_net_size.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+    lib.rf_detect_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int), C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rf_detect_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.rf_forward_heads.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.rf_postprocess.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rf_preprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.rf_profile_layers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.rf_debug_get_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p] + [C.POINTER(C.c_int)] * 3
+    lib.rf_debug_keep_all.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def model_inspect(caffemodel: str, layer: str):
+    """(w, b) folded parameters of one convolution, from the library's host-side model front end."""
+    lib = load_library()
+    dims = (C.c_int * 4)()
+    rc = lib.rf_model_inspect(caffemodel.encode(), layer.encode(), None, 0, None, 0, dims)
+    if rc != 0:
+        raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
+    shape = tuple(dims)
+    w = np.empty(shape, dtype=np.float32)
+    b = np.empty(shape[0], dtype=np.float32)
+    rc = lib.rf_model_inspect(caffemodel.encode(), layer.encode(), w.ctypes.data_as(C.c_void_p), w.size,
+                              b.ctypes.data_as(C.c_void_p), b.size, dims)
+    if rc != 0:
+        raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
+    return w, b
+
+
+STRIDES = (32, 16, 8)
+
+
+def head_shapes(net_h: int, net_w: int) -> List[Tuple[int, int, int]]:
+    return [(c, net_h // s, net_w // s) for s in STRIDES for c in (4, 8, 20)]
+
+
+class Engine:
+    """One rf_handle: one GPU, one stream."""
+
+    def __init__(self, caffemodel: str, net_h: int, net_w: int, precision: int = RF_PREC_FP16, max_batch: int = 8,
+                 max_faces: int = 256, device: int = 0, int8_table: Optional[str] = None,
+                 max_image: Optional[Tuple[int, int]] = None, flags: int = 0):
+        self.lib = load_library()
+        cfg = _Config(caffemodel.encode(), int8_table.encode() if int8_table else None, precision, net_w, net_h,
+                      max_batch, max_faces, device, max_image[1] if max_image else 0, max_image[0] if max_image else 0, flags)
+        h = C.c_void_p()
+        rc = self.lib.rf_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise RfError(rc, (self.lib.rf_last_error(None) or b"").decode())
+        self.h = h
+        self.net_h, self.net_w = net_h, net_w
+        self.max_batch, self.precision, self.device = max_batch, precision, device
+        mf = C.c_int()
+        self.lib.rf_get_net_size(self.h, None, None, None, C.byref(mf))
+        self.max_faces = mf.value
+        self.num_anchors = self.lib.rf_num_anchors(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc < 0:
+            raise RfError(rc, (self.lib.rf_last_error(self.h) or b"").decode())
+        return rc
+
+    # -- buffers --------------------------------------------------------------------------
+    def pinned_input(self) -> np.ndarray:
+        """numpy view of the library's pinned staging: (max_batch, H, W, 3) u8."""
+        p = self.lib.rf_pinned_input(self.h)
+        n = self.max_batch * self.net_h * self.net_w * 3
+        buf = (C.c_uint8 * n).from_address(p)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.max_batch, self.net_h, self.net_w, 3)
+
+    def device_input_ptr(self) -> int:
+        return int(self.lib.rf_device_input(self.h))
+
+    def stream_ptr(self) -> int:
+        return int(self.lib.rf_stream(self.h) or 0)
+
+    def synchronize(self):
+        self._check(self.lib.rf_synchronize(self.h))
+
+    # -- end to end ------------------------------------------------------------------------
+    def detect_batch(self, images: Sequence[np.ndarray], thr: float, nms_thr: float, want_index: bool = False):
+        """images: u8 BGR HWC arrays (any size <= max_image).  Returns list of (k,15) float32 arrays
+        (FaceDetectInfo rows, score order) [+ list of anchor-index arrays]."""
+        n = len(images)
+        keep = [np.ascontiguousarray(im, dtype=np.uint8) if not (im.flags.c_contiguous and im.dtype == np.uint8) else im
+                for im in images]
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in keep])
+        ws = (C.c_int * n)(*[im.shape[1] for im in keep])
+        hs = (C.c_int * n)(*[im.shape[0] for im in keep])
+        faces = np.empty((n, self.max_faces, FACE_FLOATS), dtype=np.float32)
+        counts = np.zeros(n, dtype=np.int32)
+        idx = np.empty((n, self.max_faces), dtype=np.int32) if want_index else None
+        self._check(self.lib.rf_detect_batch(self.h, ptrs, ws, hs, None, n, thr, nms_thr, faces.ctypes.data,
+                                             counts.ctypes.data, idx.ctypes.data if want_index else None))
+        out = [faces[i, :counts[i]].copy() for i in range(n)]
+        if want_index:
+            return out, [idx[i, :counts[i]].copy() for i in range(n)]
+        return out
+
+    def detect_pinned(self, n: int, thr: float, nms_thr: float, faces: np.ndarray, counts: np.ndarray):
+        """Hot-loop variant for bench.py: the n images are already in pinned_input(); results go
+        into caller-provided arrays.  Still the full H2D -> GPU -> D2H path."""
+        base = self.lib.rf_pinned_input(self.h)
+        sz = self.net_h * self.net_w * 3
+        if not hasattr(self, "_pin_args") or self._pin_args[0] != n:
+            self._pin_args = (n, (C.c_void_p * n)(*[base + i * sz for i in range(n)]),
+                              (C.c_int * n)(*[self.net_w] * n), (C.c_int * n)(*[self.net_h] * n))
+        _, ptrs, ws, hs = self._pin_args
+        self._check(self.lib.rf_detect_batch(self.h, ptrs, ws, hs, None, n, thr, nms_thr, faces.ctypes.data,
+                                             counts.ctypes.data, None))
+
+    def detect_device(self, n: int, thr: float, nms_thr: float, dev_ptr: Optional[int] = None):
+        """Asynchronous device-resident detect.  Returns (dets_ptr, counts_ptr) device addresses."""
+        d, c = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.rf_detect_batch_device(self.h, dev_ptr if dev_ptr is not None else self.device_input_ptr(),
+                                                    n, thr, nms_thr, C.byref(d), C.byref(c)))
+        return int(d.value), int(c.value)
+
+    # -- parity entry points -----------------------------------------------------------------
+    def forward_heads(self, images: np.ndarray) -> List[np.ndarray]:
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        n = images.shape[0]
+        assert images.shape[1:] == (self.net_h, self.net_w, 3), images.shape
+        outs = [np.empty((n,) + s, dtype=np.float32) for s in head_shapes(self.net_h, self.net_w)]
+        ptrs = (C.c_void_p * 9)(*[o.ctypes.data for o in outs])
+        self._check(self.lib.rf_forward_heads(self.h, images.ctypes.data, n, ptrs))
+        return outs
+
+    def postprocess(self, heads: Sequence[np.ndarray], thr: float, nms_thr: float):
+        """heads: 9 arrays (n,C,h,w).  Returns (faces list, index list, candidate counts)."""
+        keep = [np.ascontiguousarray(h, dtype=np.float32) for h in heads]
+        n = keep[0].shape[0]
+        ptrs = (C.c_void_p * 9)(*[k.ctypes.data for k in keep])
+        faces = np.empty((n, self.max_faces, FACE_FLOATS), dtype=np.float32)
+        idx = np.empty((n, self.max_faces), dtype=np.int32)
+        counts = np.zeros(n, dtype=np.int32)
+        ncand = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.rf_postprocess(self.h, ptrs, n, thr, nms_thr, faces.ctypes.data, counts.ctypes.data,
+                                            idx.ctypes.data, ncand.ctypes.data))
+        return ([faces[i, :counts[i]].copy() for i in range(n)], [idx[i, :counts[i]].copy() for i in range(n)], ncand)
+
+    def preprocess(self, img: np.ndarray) -> np.ndarray:
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        out = np.empty((self.net_h, self.net_w, 3), dtype=np.uint8)
+        self._check(self.lib.rf_preprocess(self.h, img.ctypes.data, img.shape[1], img.shape[0], 0, out.ctypes.data))
+        return out
+
+    def debug_keep_all(self):
+        self._check(self.lib.rf_debug_keep_all(self.h))
+
+    def debug_tensor(self, name: str, n: int) -> np.ndarray:
+        c, hh, ww = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.rf_debug_get_tensor(self.h, name.encode(), n, None, C.byref(c), C.byref(hh), C.byref(ww)))
+        out = np.empty((n, c.value, hh.value, ww.value), dtype=np.float32)
+        self._check(self.lib.rf_debug_get_tensor(self.h, name.encode(), n, out.ctypes.data, C.byref(c), C.byref(hh), C.byref(ww)))
+        return out
+
+    def launches_per_batch(self, n: int) -> int:
+        return self._check(self.lib.rf_launches_per_batch(self.h, n))
+
+    def profile_layers(self, n: int, iters: int = 20):
+        cap = 128
+        names = C.create_string_buffer(64 * cap)
+        ms = (C.c_float * cap)()
+        by = (C.c_double * cap)()
+        fl = (C.c_double * cap)()
+        k = self._check(self.lib.rf_profile_layers(self.h, n, iters, names, ms, by, fl, cap))
+        out = []
+        for i in range(k):
+            nm = names.raw[64 * i:64 * (i + 1)].split(b"\0", 1)[0].decode()
+            out.append(dict(name=nm, ms=float(ms[i]), bytes=float(by[i]), flops=float(fl[i])))
+        return out

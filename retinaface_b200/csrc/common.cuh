@@ -1,0 +1,55 @@
+// common.cuh -- shared device/host helpers of librf_b200 (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rf_b200.h"
+
+namespace rf {
+
+// ---- element type helpers (activations are NHWC in T = float or __half) --------------------
+template <typename T> struct Vec8;  // 8 consecutive channels
+template <> struct Vec8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float *p) { a = *reinterpret_cast<const float4 *>(p); b = *reinterpret_cast<const float4 *>(p + 4); }
+    __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = a; *reinterpret_cast<float4 *>(p + 4) = b; }
+    __device__ __forceinline__ void to_float(float f[8]) const { f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w; }
+    __device__ __forceinline__ void from_float(const float f[8]) { a = make_float4(f[0], f[1], f[2], f[3]); b = make_float4(f[4], f[5], f[6], f[7]); }
+};
+template <> struct Vec8<__half> {
+    uint4 v;
+    __device__ __forceinline__ void load(const __half *p) { v = *reinterpret_cast<const uint4 *>(p); }
+    __device__ __forceinline__ void store(__half *p) const { *reinterpret_cast<uint4 *>(p) = v; }
+    __device__ __forceinline__ void to_float(float f[8]) const {
+        const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    }
+    __device__ __forceinline__ void from_float(const float f[8]) {
+        __half2 *h = reinterpret_cast<__half2 *>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    }
+};
+
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
+
+// ---- post-process shared structures -------------------------------------------------------
+struct LevelDesc {           // one FPN level of one launch
+    int stride, h, w;        // feature map size
+    int anchor_base;         // emission index of (num 0, j 0) of this level
+    int pix_base;            // first pixel id of this level in the fused per-image pixel range
+    float base[8];           // 2 base anchors x (x1,y1,x2,y2)
+};
+struct PostParams {          // device-resident: a replayed CUDA graph picks up new values without re-capture
+    float score_thr;
+    float nms_thr;
+    const uint8_t *input;    // [n][net_h][net_w][3] u8 BGR images of this run (library buffer or caller's)
+};
+
+}  // namespace rf

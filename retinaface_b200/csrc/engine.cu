@@ -1,0 +1,920 @@
+// engine.cu -- the handle behind include/rf_b200.h: model upload, layer plan, activation arena,
+// CUDA-graph executor and the C-ABI entry points.
+//
+// Replaces the reference's engine slot: TrtNetBase / TrtRetinaFaceNet
+// (retinaface/tensorrt/trtnetbase.cpp:199-330, trtretinafacenet.cpp:48-210) and the detect
+// orchestration of RetinaFace::detect / detectBatchImages (retinaface/RetinaFace.cpp:576-940).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_simt.cuh"
+#include "model.h"
+#include "postproc.cuh"
+#include "preprocess.cuh"
+
+using namespace rf;
+
+#define RF_STR2(x) #x
+#define RF_STR(x) RF_STR2(x)
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaFail { cudaError_t e; const char *what; const char *file; int line; };
+#define CK(call)                                                        \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) throw CudaFail{_e, #call, __FILE__, __LINE__}; \
+    } while (0)
+
+std::string fmt(const char *f, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+
+struct TensorInfo {
+    std::string name;
+    int h = 0, w = 0, c = 0;
+    size_t bytes_per_img = 0;
+    int first = -1, last = -1;
+    size_t offset = 0;  // bytes into the arena (already scaled by max_batch)
+};
+
+struct Step {
+    std::string name;
+    std::vector<int> in, out;
+    std::function<void(int /*n*/, cudaStream_t)> launch;
+    double flops_per_img = 0, bytes_per_img = 0;  // algorithmic
+};
+
+}  // namespace
+
+struct rf_handle_s {
+    rf_config cfg{};
+    std::string caffemodel, table;
+    std::string err;
+    Model model;
+    std::map<std::string, float> int8_scales;
+    int device = 0;
+    int elem = 4;  // bytes per activation element
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    std::vector<TensorInfo> tensors;
+    std::map<std::string, int> tensor_by_name;
+    std::vector<Step> steps;
+    int head_step = -1;
+    unsigned char *arena = nullptr;
+    size_t arena_bytes = 0;
+
+    // weights
+    std::vector<float> wstage;  // host staging of all fp32 weights
+    float *d_weights = nullptr;
+
+    // io
+    uint8_t *d_input = nullptr;       // [max_batch][H][W][3] u8 BGR
+    uint8_t *h_input = nullptr;       // pinned mirror
+    uint8_t *d_raw = nullptr;         // one raw caller image (max_image) for the letterbox kernel
+    uint8_t *h_raw = nullptr;         // pinned
+    size_t raw_bytes = 0;
+    PostParams *d_params = nullptr, *h_params = nullptr;
+    PostBuffers pb{};
+    LevelDesc lv[3];
+    HeadWeights hw[3];
+    int feat_tensor[3] = {-1, -1, -1};
+    float *d_blobs[9] = {nullptr};    // rf_forward_heads / rf_postprocess staging (device)
+    size_t blob_elems[9] = {0};       // per image
+    rf_det *h_dets = nullptr;         // pinned [max_batch][max_faces]
+    int *h_counts = nullptr;          // pinned [2*max_batch]: kept, candidates
+    std::map<int, cudaGraphExec_t> graphs;
+    bool blobs_in_plan = false;       // head step writes blobs (forward_heads path)
+    static constexpr int kParamSlots = 1024;
+    unsigned param_seq = 0;
+    float cur_thr = 0.5f, cur_nms = 0.4f;
+
+    void *tptr(int id) const { return arena + tensors[id].offset; }
+};
+
+namespace {
+
+int fail(rf_handle h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+int fail_cuda(rf_handle h, const CudaFail &f) {
+    return fail(h, RF_ERR_CUDA, fmt("%s failed: %s (%s:%d)", f.what, cudaGetErrorString(f.e), f.file, f.line));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plan builder
+// ---------------------------------------------------------------------------------------------
+struct Builder {
+    rf_handle h;
+    int H, W;
+    size_t add_weights(const std::vector<float> &v) {
+        size_t off = h->wstage.size();
+        h->wstage.insert(h->wstage.end(), v.begin(), v.end());
+        while (h->wstage.size() % 4) h->wstage.push_back(0.f);  // keep float4 alignment
+        return off;
+    }
+    int tensor(const std::string &name, int hh, int ww, int c) {
+        TensorInfo t;
+        t.name = name; t.h = hh; t.w = ww; t.c = c;
+        t.bytes_per_img = (size_t)hh * ww * c * h->elem;
+        h->tensors.push_back(t);
+        h->tensor_by_name[name] = (int)h->tensors.size() - 1;
+        return (int)h->tensors.size() - 1;
+    }
+    void alias(const std::string &name, int id) { h->tensor_by_name[name] = id; }
+    void step(Step s) { h->steps.push_back(std::move(s)); }
+};
+
+// GEMM weight matrix [K = (tap, cin)][N] from conv weights [cout][cin][k][k]; several convs that
+// share an input are concatenated along N (det_conv1 + context_conv1, context_conv2 + conv3_1).
+std::vector<float> pack_gemm(const std::vector<const FoldedConv *> &cs, std::vector<float> &bias) {
+    const int cin = cs[0]->cin, k = cs[0]->k;
+    int N = 0;
+    for (auto c : cs) N += c->cout;
+    std::vector<float> w((size_t)k * k * cin * N);
+    bias.assign(N, 0.f);
+    int n0 = 0;
+    for (auto c : cs) {
+        for (int o = 0; o < c->cout; o++) {
+            bias[n0 + o] = c->b[o];
+            for (int ci = 0; ci < cin; ci++)
+                for (int t = 0; t < k * k; t++)
+                    w[((size_t)t * cin + ci) * N + n0 + o] = c->w[((size_t)o * cin + ci) * k * k + t];
+        }
+        n0 += c->cout;
+    }
+    return w;
+}
+
+template <typename T>
+void launch_gemm(const T *in, int ldin, int cin, const float *wk, const float *bias, int N, int ks, OutSplit<T> outs,
+                 int n, int H, int W, cudaStream_t s) {
+    long M = (long)n * H * W;
+    int bn = (N % 64 == 0) ? 64 : (N % 32 == 0 ? 32 : 16);
+    dim3 grid((unsigned)((M + 63) / 64), (N + bn - 1) / bn);
+#define RF_GEMM(BN_, KS_) k_conv_gemm<T, BN_, KS_><<<grid, 256, 0, s>>>(in, ldin, cin, wk, bias, N, outs, n, H, W)
+    if (ks == 1) { if (bn == 64) RF_GEMM(64, 1); else if (bn == 32) RF_GEMM(32, 1); else RF_GEMM(16, 1); }
+    else { if (bn == 64) RF_GEMM(64, 3); else if (bn == 32) RF_GEMM(32, 3); else RF_GEMM(16, 3); }
+#undef RF_GEMM
+}
+
+template <typename T>
+void build_plan(rf_handle h) {
+    Builder B{h, h->cfg.net_h, h->cfg.net_w};
+    const Model &m = h->model;
+    const int H = h->cfg.net_h, W = h->cfg.net_w;
+    auto T_ = [h](int id) { return reinterpret_cast<T *>(h->tptr(id)); };
+    auto Wd = [h](size_t off) { return h->d_weights + off; };
+    const double es = h->elem;
+
+    // ---- conv0 (prototxt:11-53) -----------------------------------------------------------
+    int cur_h = H / 2, cur_w = W / 2, cur_c = 8;
+    int cur = B.tensor("mobilenet0_relu0_fwd", cur_h, cur_w, 8);
+    {
+        const FoldedConv &c = m.conv("mobilenet0_conv0_fwd");
+        std::vector<float> wk(27 * 8);
+        for (int o = 0; o < 8; o++)
+            for (int cb = 0; cb < 3; cb++)       // cb: BGR channel of the u8 image; network channel = 2 - cb (RGB)
+                for (int t = 0; t < 9; t++) wk[(t * 3 + cb) * 8 + o] = c.w[((size_t)o * 3 + (2 - cb)) * 9 + t];
+        size_t ow = B.add_weights(wk), ob = B.add_weights(c.b);
+        int out = cur;
+        Step s;
+        s.name = "conv0_u8_3x3s2_bn_relu";
+        s.out = {out};
+        s.flops_per_img = 2.0 * cur_h * cur_w * 8 * 27;
+        s.bytes_per_img = (double)H * W * 3 + (double)cur_h * cur_w * 8 * es;
+        s.launch = [=](int n, cudaStream_t st) {
+            long total = (long)n * (H / 2) * (W / 2);
+            k_conv0<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->d_params, T_(out), Wd(ow), Wd(ob), n, H, W);
+        };
+        B.step(std::move(s));
+    }
+    // ---- 13 x (depthwise 3x3, pointwise 1x1) (prototxt:55-1192) -----------------------------
+    int c1 = -1, c2 = -1, c3 = -1;
+    for (int i = 1; i <= 26; i += 2) {
+        const FoldedConv &dw = m.conv("mobilenet0_conv" + std::to_string(i) + "_fwd");
+        const FoldedConv &pw = m.conv("mobilenet0_conv" + std::to_string(i + 1) + "_fwd");
+        const int C = dw.cout, S = dw.stride;
+        std::vector<float> wd(9 * C);
+        for (int c = 0; c < C; c++)
+            for (int t = 0; t < 9; t++) wd[t * C + c] = dw.w[(size_t)c * 9 + t];
+        size_t owd = B.add_weights(wd), obd = B.add_weights(dw.b);
+        const int ih = cur_h, iw = cur_w, oh = cur_h / S, ow_ = cur_w / S;
+        int tin = cur;
+        int tdw = B.tensor("mobilenet0_relu" + std::to_string(i) + "_fwd", oh, ow_, C);
+        {
+            Step s;
+            s.name = fmt("dw%d_3x3s%d_c%d", i, S, C);
+            s.in = {tin}; s.out = {tdw};
+            s.flops_per_img = 2.0 * oh * ow_ * C * 9;
+            s.bytes_per_img = ((double)ih * iw * C + (double)oh * ow_ * C) * es;
+            s.launch = [=](int n, cudaStream_t st) {
+                long total = (long)n * oh * ow_ * (C / 8);
+                unsigned g = (unsigned)((total + 255) / 256);
+                if (S == 1) k_dw3x3<T, 1><<<g, 256, 0, st>>>(T_(tin), T_(tdw), Wd(owd), Wd(obd), n, ih, iw, C);
+                else k_dw3x3<T, 2><<<g, 256, 0, st>>>(T_(tin), T_(tdw), Wd(owd), Wd(obd), n, ih, iw, C);
+            };
+            B.step(std::move(s));
+        }
+        std::vector<float> bias;
+        std::vector<float> wk = pack_gemm({&pw}, bias);
+        size_t owp = B.add_weights(wk), obp = B.add_weights(bias);
+        const int N = pw.cout;
+        int tpw = B.tensor("mobilenet0_relu" + std::to_string(i + 1) + "_fwd", oh, ow_, N);
+        {
+            Step s;
+            s.name = fmt("pw%d_1x1_%dto%d", i + 1, C, N);
+            s.in = {tdw}; s.out = {tpw};
+            s.flops_per_img = 2.0 * oh * ow_ * C * N;
+            s.bytes_per_img = ((double)oh * ow_ * C + (double)oh * ow_ * N) * es;
+            s.launch = [=](int n, cudaStream_t st) {
+                OutSplit<T> o{T_(tpw), N, N, 1, nullptr, 0, 0};
+                launch_gemm<T>(T_(tdw), C, C, Wd(owp), Wd(obp), N, 1, o, n, oh, ow_, st);
+            };
+            B.step(std::move(s));
+        }
+        cur = tpw; cur_h = oh; cur_w = ow_; cur_c = N;
+        if (i + 1 == 10) c1 = cur;
+        if (i + 1 == 22) c2 = cur;
+        if (i + 1 == 26) c3 = cur;
+    }
+    (void)cur_c;
+
+    // ---- FPN + SSH (prototxt:1199-2302) -----------------------------------------------------
+    auto conv_step = [&](const std::string &sname, std::vector<const FoldedConv *> cs, int tin, int ih, int iw,
+                         int t0, int ld0, int off0, int n0, int relu0, int t1, int ld1, int off1, int relu1) {
+        std::vector<float> bias;
+        std::vector<float> wk = pack_gemm(cs, bias);
+        size_t ow = B.add_weights(wk), ob = B.add_weights(bias);
+        const int N = (int)bias.size(), cin = cs[0]->cin, ks = cs[0]->k;
+        const int ldin = h->tensors[tin].c;
+        Step s;
+        s.name = sname;
+        s.in = {tin};
+        s.out = {t0};
+        if (t1 >= 0) s.out.push_back(t1);
+        s.flops_per_img = 2.0 * ih * iw * cin * ks * ks * N;
+        s.bytes_per_img = ((double)ih * iw * cin + (double)ih * iw * N) * es;
+        s.launch = [=](int n, cudaStream_t st) {
+            OutSplit<T> o{T_(t0) + off0, ld0, n0, relu0, t1 >= 0 ? T_(t1) + off1 : nullptr, ld1, relu1};
+            launch_gemm<T>(T_(tin), ldin, cin, Wd(ow), Wd(ob), N, ks, o, n, ih, iw, st);
+        };
+        B.step(std::move(s));
+    };
+    auto ssh = [&](const std::string &lvname, int tin, int fh, int fw, int level) {
+        const std::string p = "rf_" + lvname + "_det";
+        int cat = B.tensor(p + "_concat_relu", fh, fw, 64);
+        int ctx1 = B.tensor(p + "_context_conv1_relu", fh, fw, 16);
+        int ctx31 = B.tensor(p + "_context_conv3_1_relu", fh, fw, 16);
+        // det_conv1 (64->32, BN, ReLU after concat) + context_conv1 (64->16, BN, ReLU): one launch
+        conv_step("ssh_" + lvname + "_conv1+ctx1_3x3_64to48", {&m.conv(p + "_conv1"), &m.conv(p + "_context_conv1")}, tin, fh,
+                  fw, cat, 64, 0, 32, 1, ctx1, 16, 0, 1);
+        // context_conv2 (16->16 -> concat[32:48]) + context_conv3_1 (16->16, ReLU): one launch
+        conv_step("ssh_" + lvname + "_ctx2+ctx3_1_3x3_16to32", {&m.conv(p + "_context_conv2"), &m.conv(p + "_context_conv3_1")},
+                  ctx1, fh, fw, cat, 64, 32, 16, 1, ctx31, 16, 0, 1);
+        // context_conv3_2 (16->16 -> concat[48:64])
+        conv_step("ssh_" + lvname + "_ctx3_2_3x3_16to16", {&m.conv(p + "_context_conv3_2")}, ctx31, fh, fw, cat, 64, 48, 16, 1,
+                  -1, 0, 0, 0);
+        h->feat_tensor[level] = cat;
+        // the concat tensor is written by three steps: make it live from the first of them
+    };
+    auto upadd = [&](const std::string &name, int tlat, int tup, int fh, int fw, int which) {
+        size_t ow = B.add_weights(m.up_w[which]);
+        int out = B.tensor(name, fh, fw, 64);
+        Step s;
+        s.name = "upsample_add" + name;
+        s.in = {tlat, tup}; s.out = {out};
+        s.flops_per_img = 2.0 * fh * fw * 64 * 4;
+        s.bytes_per_img = ((double)fh * fw * 64 * 2 + (double)(fh / 2) * (fw / 2) * 64) * es;
+        s.launch = [=](int n, cudaStream_t st) {
+            long total = (long)n * fh * fw * 8;
+            k_upsample_add<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(T_(tlat), T_(tup), T_(out), Wd(ow), n, fh, fw, 64,
+                                                                           fh / 2, fw / 2);
+        };
+        B.step(std::move(s));
+        return out;
+    };
+    const int h32 = H / 32, w32 = W / 32, h16 = H / 16, w16 = W / 16, h8 = H / 8, w8 = W / 8;
+    int lat3 = B.tensor("rf_c3_lateral_relu", h32, w32, 64);
+    conv_step("c3_lateral_1x1_256to64", {&m.conv("rf_c3_lateral")}, c3, h32, w32, lat3, 64, 0, 64, 1, -1, 0, 0, 0);
+    ssh("c3", lat3, h32, w32, 0);
+    int lat2 = B.tensor("rf_c2_lateral_relu", h16, w16, 64);
+    conv_step("c2_lateral_1x1_128to64", {&m.conv("rf_c2_lateral")}, c2, h16, w16, lat2, 64, 0, 64, 1, -1, 0, 0, 0);
+    int plus0 = upadd("_plus0", lat2, lat3, h16, w16, 0);
+    int aggr2 = B.tensor("rf_c2_aggr_relu", h16, w16, 64);
+    conv_step("c2_aggr_3x3_64to64", {&m.conv("rf_c2_aggr")}, plus0, h16, w16, aggr2, 64, 0, 64, 1, -1, 0, 0, 0);
+    ssh("c2", aggr2, h16, w16, 1);
+    int lat1 = B.tensor("rf_c1_red_conv_relu", h8, w8, 64);
+    conv_step("c1_red_1x1_64to64", {&m.conv("rf_c1_red_conv")}, c1, h8, w8, lat1, 64, 0, 64, 1, -1, 0, 0, 0);
+    int plus1 = upadd("_plus1", lat1, aggr2, h8, w8, 1);
+    int aggr1 = B.tensor("rf_c1_aggr_relu", h8, w8, 64);
+    conv_step("c1_aggr_3x3_64to64", {&m.conv("rf_c1_aggr")}, plus1, h8, w8, aggr1, 64, 0, 64, 1, -1, 0, 0, 0);
+    ssh("c1", aggr1, h8, w8, 2);
+
+    // ---- predictors + decode (fused) and NMS -------------------------------------------------
+    size_t hw_off[3], hb_off[3];
+    const int strides[3] = {32, 16, 8};
+    for (int l = 0; l < 3; l++) {
+        std::string st = "_stride" + std::to_string(strides[l]);
+        const FoldedConv *cs[3] = {&m.conv("face_rpn_cls_score" + st), &m.conv("face_rpn_bbox_pred" + st),
+                                   &m.conv("face_rpn_landmark_pred" + st)};
+        std::vector<float> w(32 * 64), b(32);
+        int r = 0;
+        for (auto c : cs)
+            for (int o = 0; o < c->cout; o++, r++) {
+                b[r] = c->b[o];
+                for (int ci = 0; ci < 64; ci++) w[r * 64 + ci] = c->w[(size_t)o * 64 + ci];
+            }
+        hw_off[l] = B.add_weights(w);
+        hb_off[l] = B.add_weights(b);
+    }
+    {
+        Step s;
+        s.name = "heads_1x1+softmax+decode_all_levels";
+        s.in = {h->feat_tensor[0], h->feat_tensor[1], h->feat_tensor[2]};
+        double px = (double)h32 * w32 + (double)h16 * w16 + (double)h8 * w8;
+        s.flops_per_img = 2.0 * px * 64 * 4;   // threshold-first: only cls logits are computed for every pixel
+        s.bytes_per_img = px * 64 * es;
+        int f0 = h->feat_tensor[0], f1 = h->feat_tensor[1], f2 = h->feat_tensor[2];
+        size_t w0 = hw_off[0], w1 = hw_off[1], w2 = hw_off[2], b0 = hb_off[0], b1 = hb_off[1], b2 = hb_off[2];
+        s.launch = [=](int n, cudaStream_t st) {
+            const T *feat[3] = {T_(f0), T_(f1), T_(f2)};
+            HeadWeights hws[3] = {{Wd(w0), Wd(b0)}, {Wd(w1), Wd(b1)}, {Wd(w2), Wd(b2)}};
+            launch_head_decode<T>(feat, hws, h->lv, n, W, H, h->d_params, h->pb, h->blobs_in_plan ? h->d_blobs : nullptr, st);
+        };
+        h->head_step = (int)h->steps.size();
+        B.step(std::move(s));
+    }
+    {
+        Step s;
+        s.name = "sort+nms";
+        s.flops_per_img = 0;
+        s.bytes_per_img = 0;
+        s.launch = [=](int n, cudaStream_t st) { launch_nms(n, h->d_params, h->pb, st); };
+        B.step(std::move(s));
+    }
+}
+
+// Liveness-based first-fit placement of activation tensors in one arena.
+void place_tensors(rf_handle h, bool keep_all) {
+    auto &ts = h->tensors;
+    for (int si = 0; si < (int)h->steps.size(); si++) {
+        for (int t : h->steps[si].out) { if (ts[t].first < 0) ts[t].first = si; ts[t].last = std::max(ts[t].last, si); }
+        for (int t : h->steps[si].in) ts[t].last = std::max(ts[t].last, si);
+    }
+    const size_t B = (size_t)h->cfg.max_batch;
+    size_t top = 0;
+    std::vector<int> order(ts.size());
+    for (size_t i = 0; i < ts.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ts[a].first < ts[b].first; });
+    std::vector<int> placed;
+    for (int id : order) {
+        size_t sz = (ts[id].bytes_per_img * B + 255) / 256 * 256;
+        size_t off = 0;
+        if (keep_all) {
+            off = top;
+        } else {
+            bool moved = true;
+            while (moved) {
+                moved = false;
+                for (int p : placed) {
+                    bool live_overlap = !(ts[p].last < ts[id].first || ts[id].last < ts[p].first);
+                    size_t psz = (ts[p].bytes_per_img * B + 255) / 256 * 256;
+                    bool mem_overlap = off < ts[p].offset + psz && ts[p].offset < off + sz;
+                    if (live_overlap && mem_overlap) { off = ts[p].offset + psz; moved = true; }
+                }
+            }
+        }
+        ts[id].offset = off;
+        top = std::max(top, off + sz);
+        placed.push_back(id);
+    }
+    h->arena_bytes = top;
+}
+
+void run_steps(rf_handle h, int n, cudaStream_t s) {
+    for (auto &st : h->steps) st.launch(n, s);
+}
+
+void forward_graph(rf_handle h, int n) {
+    if (h->cfg.flags & RF_FLAG_NO_GRAPH) {
+        run_steps(h, n, h->stream);
+        CK(cudaGetLastError());
+        return;
+    }
+    auto it = h->graphs.find(n);
+    if (it == h->graphs.end()) {
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        run_steps(h, n, h->stream);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        if (e != cudaSuccess) throw CudaFail{e, "cudaStreamEndCapture", __FILE__, __LINE__};
+        cudaGraphExec_t ge = nullptr;
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) throw CudaFail{e, "cudaGraphInstantiate", __FILE__, __LINE__};
+        it = h->graphs.emplace(n, ge).first;
+    }
+    CK(cudaGraphLaunch(it->second, h->stream));
+}
+
+// Run parameters travel through a small ring of pinned slots so that an asynchronous caller
+// (rf_detect_batch_device) can queue several runs without overwriting a copy still in flight.
+void set_params(rf_handle h, float thr, float nms, const uint8_t *input = nullptr) {
+    PostParams *slot = h->h_params + (h->param_seq++ % rf_handle_s::kParamSlots);
+    slot->score_thr = thr;
+    slot->nms_thr = nms;
+    slot->input = input ? input : h->d_input;
+    h->cur_thr = thr;
+    h->cur_nms = nms;
+    CK(cudaMemcpyAsync(h->d_params, slot, sizeof(PostParams), cudaMemcpyHostToDevice, h->stream));
+}
+
+void destroy(rf_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->arena); cudaFree(h->d_weights); cudaFree(h->d_input); cudaFree(h->d_raw); cudaFree(h->d_params);
+    cudaFree(h->pb.cand_keys); cudaFree(h->pb.cand_recs); cudaFree(h->pb.cand_count); cudaFree(h->pb.sort_scratch);
+    cudaFree(h->pb.flag_scratch); cudaFree(h->pb.out_dets); cudaFree(h->pb.out_counts); cudaFree(h->pb.out_total_kept);
+    for (auto p : h->d_blobs) cudaFree(p);
+    cudaFreeHost(h->h_input); cudaFreeHost(h->h_raw); cudaFreeHost(h->h_params); cudaFreeHost(h->h_dets); cudaFreeHost(h->h_counts);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int check_n(rf_handle h, int n) {
+    if (!h) return RF_ERR_INVALID_ARG;
+    if (n < 0) return fail(h, RF_ERR_INVALID_ARG, "negative batch size");
+    if (n > h->cfg.max_batch) return fail(h, RF_ERR_CAPACITY, fmt("batch %d exceeds max_batch %d", n, h->cfg.max_batch));
+    return RF_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int rf_abi_version(void) { return RF_B200_ABI_VERSION; }
+
+const char *rf_build_info(void) {
+    return "librf_b200 (RetinaFace mnet25 detect path) built for sm_100a, CUDA " RF_STR(CUDART_VERSION);
+}
+
+const char *rf_status_string(int s) {
+    switch (s) {
+        case RF_OK: return "ok";
+        case RF_ERR_INVALID_ARG: return "invalid argument";
+        case RF_ERR_IO: return "i/o error";
+        case RF_ERR_MODEL: return "model error";
+        case RF_ERR_CUDA: return "CUDA error";
+        case RF_ERR_NO_DEVICE: return "no usable CUDA device (the library has no CPU path)";
+        case RF_ERR_CAPACITY: return "capacity exceeded";
+        case RF_ERR_UNSUPPORTED: return "unsupported";
+    }
+    return "unknown status";
+}
+
+const char *rf_last_error(rf_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rf_create(const rf_config *cfg, rf_handle *out) {
+    if (out) *out = nullptr;
+    if (!cfg || !out) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_create: cfg and out must be non-NULL");
+    if (!cfg->caffemodel_path) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_create: caffemodel_path is NULL");
+    if (cfg->net_w <= 0 || cfg->net_h <= 0 || cfg->net_w % 32 || cfg->net_h % 32)
+        return fail(nullptr, RF_ERR_INVALID_ARG, fmt("rf_create: net size %dx%d must be positive multiples of 32", cfg->net_w, cfg->net_h));
+    if (cfg->max_batch <= 0 || cfg->max_batch > 4096) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_create: max_batch must be in [1, 4096]");
+    if (cfg->precision != RF_PREC_FP32 && cfg->precision != RF_PREC_FP16 && cfg->precision != RF_PREC_INT8)
+        return fail(nullptr, RF_ERR_INVALID_ARG, "rf_create: unknown precision");
+    if (cfg->precision == RF_PREC_INT8) return fail(nullptr, RF_ERR_UNSUPPORTED, "rf_create: INT8 path is not built yet");
+
+    std::unique_ptr<rf_handle_s, void (*)(rf_handle)> H(new rf_handle_s, destroy);
+    rf_handle h = H.get();
+    h->cfg = *cfg;
+    h->caffemodel = cfg->caffemodel_path;
+    h->cfg.caffemodel_path = h->caffemodel.c_str();
+    if (cfg->int8_table_path) { h->table = cfg->int8_table_path; h->cfg.int8_table_path = h->table.c_str(); }
+    if (h->cfg.max_faces <= 0) h->cfg.max_faces = 256;
+    if (h->cfg.max_faces > 8192) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_create: max_faces must be <= 8192");
+    if (h->cfg.max_image_w <= 0) h->cfg.max_image_w = h->cfg.net_w;
+    if (h->cfg.max_image_h <= 0) h->cfg.max_image_h = h->cfg.net_h;
+    h->cfg.max_image_w = std::max(h->cfg.max_image_w, h->cfg.net_w);
+    h->cfg.max_image_h = std::max(h->cfg.max_image_h, h->cfg.net_h);
+    h->device = cfg->device;
+    h->elem = cfg->precision == RF_PREC_FP32 ? 4 : 2;
+
+    // ---- model (host) --------------------------------------------------------------------
+    {
+        std::vector<RawLayer> layers;
+        std::string err;
+        bool io = false;
+        if (!read_caffemodel(h->caffemodel, layers, err, io)) return fail(nullptr, io ? RF_ERR_IO : RF_ERR_MODEL, err);
+        if (!build_mnet_model(layers, h->model, err)) return fail(nullptr, RF_ERR_MODEL, err);
+        if (!h->table.empty() && !read_int8_table(h->table, h->int8_scales, err)) return fail(nullptr, RF_ERR_IO, err);
+    }
+    // ---- device ----------------------------------------------------------------------------
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, RF_ERR_NO_DEVICE, fmt("no CUDA device (%s); librf_b200 has no CPU path", e == cudaSuccess ? "count 0" : cudaGetErrorString(e)));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, RF_ERR_INVALID_ARG, fmt("device %d out of range (%d devices)", cfg->device, ndev));
+    try {
+        CK(cudaSetDevice(h->device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, h->device));
+        if (prop.major != 10)
+            return fail(nullptr, RF_ERR_NO_DEVICE, fmt("device %d is sm_%d%d; librf_b200 is built for sm_100a only", h->device, prop.major, prop.minor));
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&h->ev0));
+        CK(cudaEventCreate(&h->ev1));
+        CK(postproc_init());
+
+        const int Hn = h->cfg.net_h, Wn = h->cfg.net_w, Bm = h->cfg.max_batch;
+        // levels / anchors
+        const int strides[3] = {32, 16, 8};
+        int abase = 0, pbase = 0;
+        for (int l = 0; l < 3; l++) {
+            LevelDesc &lv = h->lv[l];
+            lv.stride = strides[l]; lv.h = Hn / strides[l]; lv.w = Wn / strides[l];
+            lv.anchor_base = abase; lv.pix_base = pbase;
+            base_anchors_net3(strides[l], lv.base);
+            abase += 2 * lv.h * lv.w; pbase += lv.h * lv.w;
+        }
+        const int A = abase;
+        int ap2 = 1;
+        while (ap2 < A) ap2 <<= 1;
+
+        if (h->cfg.precision == RF_PREC_FP32) build_plan<float>(h); else build_plan<__half>(h);
+        place_tensors(h, false);
+        CK(cudaMalloc(&h->arena, h->arena_bytes));
+        CK(cudaMalloc(&h->d_weights, h->wstage.size() * sizeof(float)));
+        CK(cudaMemcpy(h->d_weights, h->wstage.data(), h->wstage.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+        const size_t in_bytes = (size_t)Bm * Hn * Wn * 3;
+        CK(cudaMalloc(&h->d_input, in_bytes));
+        CK(cudaHostAlloc(&h->h_input, in_bytes, cudaHostAllocDefault));
+        h->raw_bytes = (size_t)h->cfg.max_image_w * h->cfg.max_image_h * 3;
+        CK(cudaMalloc(&h->d_raw, h->raw_bytes));
+        CK(cudaHostAlloc(&h->h_raw, h->raw_bytes, cudaHostAllocDefault));
+        CK(cudaMalloc(&h->d_params, sizeof(PostParams)));
+        CK(cudaHostAlloc(&h->h_params, sizeof(PostParams) * rf_handle_s::kParamSlots, cudaHostAllocDefault));
+
+        PostBuffers &pb = h->pb;
+        pb.anchors_per_image = A; pb.anchors_pow2 = ap2; pb.max_faces = h->cfg.max_faces;
+        CK(cudaMalloc(&pb.cand_keys, sizeof(unsigned long long) * (size_t)Bm * A));
+        CK(cudaMalloc(&pb.cand_recs, sizeof(rf_det) * (size_t)Bm * A));
+        CK(cudaMalloc(&pb.cand_count, sizeof(int) * Bm));
+        CK(cudaMemset(pb.cand_count, 0, sizeof(int) * Bm));
+        CK(cudaMalloc(&pb.sort_scratch, sizeof(unsigned long long) * (size_t)Bm * ap2));
+        CK(cudaMalloc(&pb.flag_scratch, (size_t)Bm * ap2));
+        CK(cudaMalloc(&pb.out_dets, sizeof(rf_det) * (size_t)Bm * pb.max_faces));
+        CK(cudaMalloc(&pb.out_counts, sizeof(int) * Bm));
+        CK(cudaMalloc(&pb.out_total_kept, sizeof(int) * Bm));
+        CK(cudaMemset(pb.out_counts, 0, sizeof(int) * Bm));
+        CK(cudaHostAlloc(&h->h_dets, sizeof(rf_det) * (size_t)Bm * pb.max_faces, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&h->h_counts, sizeof(int) * 2 * Bm, cudaHostAllocDefault));
+        for (int l = 0; l < 3; l++) {
+            const int ch[3] = {4, 8, 20};
+            for (int k = 0; k < 3; k++) h->blob_elems[3 * l + k] = (size_t)ch[k] * h->lv[l].h * h->lv[l].w;
+        }
+        CK(cudaDeviceSynchronize());
+    } catch (const CudaFail &f) {
+        return fail_cuda(nullptr, f);
+    }
+    *out = H.release();
+    return RF_OK;
+}
+
+void rf_destroy(rf_handle h) { destroy(h); }
+
+uint8_t *rf_pinned_input(rf_handle h) { return h ? h->h_input : nullptr; }
+uint8_t *rf_device_input(rf_handle h) { return h ? h->d_input : nullptr; }
+
+int rf_get_net_size(rf_handle h, int *net_w, int *net_h, int *max_batch, int *max_faces) {
+    if (!h) return RF_ERR_INVALID_ARG;
+    if (net_w) *net_w = h->cfg.net_w;
+    if (net_h) *net_h = h->cfg.net_h;
+    if (max_batch) *max_batch = h->cfg.max_batch;
+    if (max_faces) *max_faces = h->cfg.max_faces;
+    return RF_OK;
+}
+int rf_num_anchors(rf_handle h) { return h ? h->pb.anchors_per_image : RF_ERR_INVALID_ARG; }
+void *rf_stream(rf_handle h) { return h ? (void *)h->stream : nullptr; }
+
+int rf_synchronize(rf_handle h) {
+    if (!h) return RF_ERR_INVALID_ARG;
+    try { CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream)); } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+int rf_launches_per_batch(rf_handle h, int n) {
+    (void)n;
+    return h ? (int)h->steps.size() : RF_ERR_INVALID_ARG;
+}
+
+int rf_detect_batch_device(rf_handle h, const uint8_t *dev_bgr, int n, float thr, float nms, const rf_det **dev_dets,
+                           const int32_t **dev_counts) {
+    int rc = check_n(h, n);
+    if (rc) return rc;
+    try {
+        CK(cudaSetDevice(h->device));
+        // the caller's device images are read in place (conv0 takes the pointer from the run parameters)
+        if (h->param_seq && h->param_seq % rf_handle_s::kParamSlots == 0) CK(cudaStreamSynchronize(h->stream));
+        set_params(h, thr, nms, dev_bgr);
+        if (n > 0) forward_graph(h, n);
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    if (dev_dets) *dev_dets = h->pb.out_dets;
+    if (dev_counts) *dev_counts = h->pb.out_counts;
+    return RF_OK;
+}
+
+static int fetch_results(rf_handle h, int n, rf_face *out_faces, int *out_counts, int32_t *out_idx, int *out_ncand) {
+    const int mf = h->cfg.max_faces;
+    CK(cudaMemcpyAsync(h->h_counts, h->pb.out_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_dets, h->pb.out_dets, sizeof(rf_det) * (size_t)n * mf, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; i++) {
+        int k = h->h_counts[i];
+        if (out_counts) out_counts[i] = k;
+        for (int j = 0; j < k; j++) {
+            const rf_det &d = h->h_dets[(size_t)i * mf + j];
+            if (out_faces) out_faces[(size_t)i * mf + j] = d.face;
+            if (out_idx) out_idx[(size_t)i * mf + j] = d.anchor_index;
+        }
+    }
+    (void)out_ncand;
+    return RF_OK;
+}
+
+int rf_detect_batch(rf_handle h, const uint8_t *const *imgs, const int *widths, const int *heights, const int *row_strides,
+                    int n, float thr, float nms, rf_face *out_faces, int *out_counts, int32_t *out_idx) {
+    int rc = check_n(h, n);
+    if (rc) return rc;
+    if (n == 0) return RF_OK;
+    if (!imgs || !widths || !heights) return fail(h, RF_ERR_INVALID_ARG, "rf_detect_batch: NULL image arrays");
+    const int Hn = h->cfg.net_h, Wn = h->cfg.net_w;
+    const size_t img_bytes = (size_t)Hn * Wn * 3;
+    try {
+        CK(cudaSetDevice(h->device));
+        // Network-sized packed images are copied H2D straight from the caller's memory when it is
+        // pinned (cudaHostAlloc / cudaHostRegister / the library's own rf_pinned_input), otherwise via the
+        // library's pinned mirror; runs of adjacent sources collapse into one copy.  Other sizes are
+        // letter-boxed on the GPU one by one (preprocess.cuh).
+        const uint8_t *run_src = nullptr;
+        int run_start = -1, run_len = 0;
+        auto flush = [&]() {
+            if (run_start < 0) return;
+            CK(cudaMemcpyAsync(h->d_input + (size_t)run_start * img_bytes, run_src, (size_t)run_len * img_bytes,
+                               cudaMemcpyHostToDevice, h->stream));
+            run_start = -1;
+        };
+        bool staging_dirty = false;
+        for (int i = 0; i < n; i++) {
+            if (!imgs[i] || widths[i] <= 0 || heights[i] <= 0) { return fail(h, RF_ERR_INVALID_ARG, fmt("rf_detect_batch: image %d is empty", i)); }
+            const int rs = row_strides && row_strides[i] ? row_strides[i] : widths[i] * 3;
+            if (widths[i] == Wn && heights[i] == Hn && rs == Wn * 3) {
+                const uint8_t *src = imgs[i];
+                const bool in_mirror = src >= h->h_input && src < h->h_input + (size_t)h->cfg.max_batch * img_bytes;
+                if (!in_mirror) {
+                    cudaPointerAttributes at{};
+                    bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+                    if (!pinned) {
+                        cudaGetLastError();
+                        if (!staging_dirty) { CK(cudaStreamSynchronize(h->stream)); staging_dirty = true; }
+                        uint8_t *slot = h->h_input + (size_t)i * img_bytes;
+                        memcpy(slot, src, img_bytes);
+                        src = slot;
+                    }
+                }
+                if (run_start >= 0 && src == run_src + (size_t)run_len * img_bytes) { run_len++; }
+                else { flush(); run_start = i; run_src = src; run_len = 1; }
+            } else {
+                flush();
+                if (widths[i] > h->cfg.max_image_w || heights[i] > h->cfg.max_image_h)
+                    return fail(h, RF_ERR_CAPACITY, fmt("image %d is %dx%d, larger than max_image %dx%d", i, widths[i], heights[i],
+                                                        h->cfg.max_image_w, h->cfg.max_image_h));
+                CK(cudaStreamSynchronize(h->stream));  // h_raw is single-buffered
+                for (int y = 0; y < heights[i]; y++) memcpy(h->h_raw + (size_t)y * widths[i] * 3, imgs[i] + (size_t)y * rs, (size_t)widths[i] * 3);
+                CK(cudaMemcpyAsync(h->d_raw, h->h_raw, (size_t)widths[i] * heights[i] * 3, cudaMemcpyHostToDevice, h->stream));
+                launch_letterbox(h->d_raw, widths[i], heights[i], h->d_input + (size_t)i * img_bytes, Wn, Hn, h->stream);
+            }
+        }
+        flush();
+        set_params(h, thr, nms);
+        forward_graph(h, n);
+        fetch_results(h, n, out_faces, out_counts, out_idx, nullptr);
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+int rf_preprocess(rf_handle h, const uint8_t *bgr, int width, int height, int row_stride, uint8_t *out) {
+    if (!h || !bgr || !out || width <= 0 || height <= 0) return fail(h, RF_ERR_INVALID_ARG, "rf_preprocess: bad arguments");
+    if (width > h->cfg.max_image_w || height > h->cfg.max_image_h) return fail(h, RF_ERR_CAPACITY, "rf_preprocess: image larger than max_image");
+    const int Hn = h->cfg.net_h, Wn = h->cfg.net_w;
+    const int rs = row_stride ? row_stride : width * 3;
+    try {
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int y = 0; y < height; y++) memcpy(h->h_raw + (size_t)y * width * 3, bgr + (size_t)y * rs, (size_t)width * 3);
+        CK(cudaMemcpyAsync(h->d_raw, h->h_raw, (size_t)width * height * 3, cudaMemcpyHostToDevice, h->stream));
+        launch_letterbox(h->d_raw, width, height, h->d_input, Wn, Hn, h->stream);
+        CK(cudaMemcpyAsync(h->h_input, h->d_input, (size_t)Hn * Wn * 3, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        memcpy(out, h->h_input, (size_t)Hn * Wn * 3);
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+static void ensure_blobs(rf_handle h) {
+    if (h->d_blobs[0]) return;
+    for (int i = 0; i < 9; i++) CK(cudaMalloc(&h->d_blobs[i], sizeof(float) * h->blob_elems[i] * h->cfg.max_batch));
+}
+
+int rf_forward_heads(rf_handle h, const uint8_t *bgr, int n, float *const heads_out[9]) {
+    int rc = check_n(h, n);
+    if (rc) return rc;
+    if (n == 0) return RF_OK;
+    if (!bgr || !heads_out) return fail(h, RF_ERR_INVALID_ARG, "rf_forward_heads: NULL argument");
+    try {
+        CK(cudaSetDevice(h->device));
+        ensure_blobs(h);
+        const size_t bytes = (size_t)n * h->cfg.net_h * h->cfg.net_w * 3;
+        CK(cudaStreamSynchronize(h->stream));
+        memcpy(h->h_input, bgr, bytes);
+        CK(cudaMemcpyAsync(h->d_input, h->h_input, bytes, cudaMemcpyHostToDevice, h->stream));
+        set_params(h, h->cur_thr, h->cur_nms);
+        h->blobs_in_plan = true;
+        try { run_steps(h, n, h->stream); } catch (...) { h->blobs_in_plan = false; throw; }
+        h->blobs_in_plan = false;
+        CK(cudaGetLastError());
+        for (int i = 0; i < 9; i++)
+            CK(cudaMemcpyAsync(heads_out[i], h->d_blobs[i], sizeof(float) * h->blob_elems[i] * n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+int rf_postprocess(rf_handle h, const float *const heads[9], int n, float thr, float nms, rf_face *out_faces, int *out_counts,
+                   int32_t *out_idx, int *out_ncand) {
+    int rc = check_n(h, n);
+    if (rc) return rc;
+    if (n == 0) return RF_OK;
+    if (!heads) return fail(h, RF_ERR_INVALID_ARG, "rf_postprocess: NULL heads");
+    try {
+        CK(cudaSetDevice(h->device));
+        ensure_blobs(h);
+        for (int i = 0; i < 9; i++)
+            CK(cudaMemcpyAsync(h->d_blobs[i], heads[i], sizeof(float) * h->blob_elems[i] * n, cudaMemcpyHostToDevice, h->stream));
+        set_params(h, thr, nms);
+        launch_blob_decode(h->d_blobs, h->lv, n, h->cfg.net_w, h->cfg.net_h, h->d_params, h->pb, h->stream);
+        if (out_ncand) CK(cudaMemcpyAsync(h->h_counts + h->cfg.max_batch, h->pb.cand_count, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+        launch_nms(n, h->d_params, h->pb, h->stream);
+        CK(cudaGetLastError());
+        fetch_results(h, n, out_faces, out_counts, out_idx, nullptr);
+        if (out_ncand) for (int i = 0; i < n; i++) out_ncand[i] = h->h_counts[h->cfg.max_batch + i];
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+// Debug / parity: any materialised activation by its Caffe top name, as NCHW float32.
+int rf_debug_get_tensor(rf_handle h, const char *name, int n, float *out_nchw, int *c, int *hh, int *ww) {
+    int rc = check_n(h, n);
+    if (rc) return rc;
+    auto it = h->tensor_by_name.find(name ? name : "");
+    if (it == h->tensor_by_name.end()) return fail(h, RF_ERR_INVALID_ARG, fmt("unknown tensor '%s'", name ? name : "(null)"));
+    const TensorInfo &t = h->tensors[it->second];
+    if (c) *c = t.c;
+    if (hh) *hh = t.h;
+    if (ww) *ww = t.w;
+    if (!out_nchw) return RF_OK;
+    try {
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        size_t elems = (size_t)n * t.h * t.w * t.c;
+        std::vector<unsigned char> host(elems * h->elem);
+        CK(cudaMemcpy(host.data(), h->tptr(it->second), host.size(), cudaMemcpyDeviceToHost));
+        for (int b = 0; b < n; b++)
+            for (int y = 0; y < t.h; y++)
+                for (int x = 0; x < t.w; x++)
+                    for (int ch = 0; ch < t.c; ch++) {
+                        size_t src = (((size_t)b * t.h + y) * t.w + x) * t.c + ch;
+                        float v = h->elem == 4 ? reinterpret_cast<float *>(host.data())[src]
+                                               : __half2float(reinterpret_cast<__half *>(host.data())[src]);
+                        out_nchw[(((size_t)b * t.c + ch) * t.h + y) * t.w + x] = v;
+                    }
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+// Re-places activations without buffer reuse so that rf_debug_get_tensor sees every tensor of
+// the last forward (debug only; call before the first forward).
+int rf_debug_keep_all(rf_handle h) {
+    if (!h) return RF_ERR_INVALID_ARG;
+    try {
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
+        h->graphs.clear();
+        for (auto &t : h->tensors) { t.first = -1; t.last = -1; }
+        place_tensors(h, true);
+        CK(cudaFree(h->arena));
+        h->arena = nullptr;
+        CK(cudaMalloc(&h->arena, h->arena_bytes));
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+// Host-only (no GPU needed): folded FP32 weights/bias of one convolution as the engine will hold
+// them (BatchNorm + Scale + bias folded).  dims = {cout, cin/groups, k, k}.  Lets CPU-only tests
+// check the model front end against the oracle's fold.
+int rf_model_inspect(const char *caffemodel_path, const char *layer, float *w, int wcap, float *b, int bcap, int dims[4]) {
+    if (!caffemodel_path || !layer) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_model_inspect: NULL argument");
+    std::vector<RawLayer> layers;
+    std::string err;
+    bool io = false;
+    Model m;
+    if (!read_caffemodel(caffemodel_path, layers, err, io)) return fail(nullptr, io ? RF_ERR_IO : RF_ERR_MODEL, err);
+    if (!build_mnet_model(layers, m, err)) return fail(nullptr, RF_ERR_MODEL, err);
+    auto it = m.convs.find(layer);
+    if (it == m.convs.end()) return fail(nullptr, RF_ERR_INVALID_ARG, std::string("no convolution '") + layer + "'");
+    const FoldedConv &c = it->second;
+    if (dims) { dims[0] = c.cout; dims[1] = c.cin / c.groups; dims[2] = c.k; dims[3] = c.k; }
+    if (w) { if ((size_t)wcap < c.w.size()) return fail(nullptr, RF_ERR_CAPACITY, "w buffer too small"); memcpy(w, c.w.data(), c.w.size() * 4); }
+    if (b) { if ((size_t)bcap < c.b.size()) return fail(nullptr, RF_ERR_CAPACITY, "b buffer too small"); memcpy(b, c.b.data(), c.b.size() * 4); }
+    return RF_OK;
+}
+
+int rf_profile_layers(rf_handle h, int n, int iters, char (*names)[64], float *ms, double *bytes, double *flops, int cap) {
+    int rc = check_n(h, n);
+    if (rc) return rc;
+    if (n == 0 || iters <= 0) return fail(h, RF_ERR_INVALID_ARG, "rf_profile_layers: n and iters must be positive");
+    int cnt = 0;
+    try {
+        CK(cudaSetDevice(h->device));
+        set_params(h, h->cur_thr, h->cur_nms);
+        run_steps(h, n, h->stream);  // warm everything once (also leaves consistent inputs for every step)
+        CK(cudaStreamSynchronize(h->stream));
+        for (size_t si = 0; si < h->steps.size(); si++) {
+            auto &st = h->steps[si];
+            if (cnt >= cap) break;
+            if ((int)si == h->head_step + 1) {
+                // sort+nms consumes the candidate list: give every timed launch a fresh one
+                float acc = 0;
+                for (int i = 0; i < iters; i++) {
+                    h->steps[h->head_step].launch(n, h->stream);
+                    CK(cudaEventRecord(h->ev0, h->stream));
+                    st.launch(n, h->stream);
+                    CK(cudaEventRecord(h->ev1, h->stream));
+                    CK(cudaEventSynchronize(h->ev1));
+                    float t = 0;
+                    CK(cudaEventElapsedTime(&t, h->ev0, h->ev1));
+                    acc += t;
+                }
+                snprintf(names[cnt], 64, "%s", st.name.c_str());
+                ms[cnt] = acc / iters;
+                if (bytes) bytes[cnt] = st.bytes_per_img * n;
+                if (flops) flops[cnt] = st.flops_per_img * n;
+                cnt++;
+                continue;
+            }
+            st.launch(n, h->stream);
+            CK(cudaEventRecord(h->ev0, h->stream));
+            for (int i = 0; i < iters; i++) st.launch(n, h->stream);
+            CK(cudaEventRecord(h->ev1, h->stream));
+            CK(cudaEventSynchronize(h->ev1));
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, h->ev0, h->ev1));
+            snprintf(names[cnt], 64, "%s", st.name.c_str());
+            ms[cnt] = t / iters;
+            if (bytes) bytes[cnt] = st.bytes_per_img * n;
+            if (flops) flops[cnt] = st.flops_per_img * n;
+            cnt++;
+        }
+        CK(cudaGetLastError());
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return cnt;
+}
+
+}  // extern "C"

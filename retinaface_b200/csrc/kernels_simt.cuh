@@ -1,0 +1,262 @@
+// kernels_simt.cuh -- SIMT (CUDA-core) layer kernels of librf_b200: the FP32 tight-parity path
+// and the FP16 fallback for layers that have no tcgen05 kernel.  NHWC activations, FP32
+// accumulate, folded-BN bias + optional ReLU fused into every epilogue.
+//
+// What each kernel replaces in the reference: the corresponding layers that TensorRT executes
+// inside context->enqueue (retinaface/tensorrt/trtretinafacenet.cpp:60) for the graph of
+// model/mnet-deconv-0517.prototxt (layer line numbers given per kernel).
+#pragma once
+#include "common.cuh"
+
+namespace rf {
+
+// ------------------------------------------------------------------------------------------
+// conv0: mobilenet0_conv0 (prototxt:11) 3x3 s2 p1, 3 -> 8, + BN + ReLU, consuming the u8 BGR
+// HWC image directly: the BGR->RGB swap and u8->float of convertBGR2RGBfloat / imageSplit
+// (resizeconvertion.cu:46-63,165-185) are folded into the weight order / the load.
+//   wk: [27][8] floats, row = (ky*3+kx)*3 + c_bgr ; bias [8].
+// One thread per output pixel (8 channels = one 16/32-byte store).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_conv0(const PostParams *__restrict__ run, T *__restrict__ out,
+                                               const float *__restrict__ wk, const float *__restrict__ bias,
+                                               int n, int H, int W) {
+    __shared__ float sw[27 * 8 + 8];
+    for (int i = threadIdx.x; i < 27 * 8 + 8; i += blockDim.x) sw[i] = i < 216 ? wk[i] : bias[i - 216];
+    __syncthreads();
+    const int OH = H >> 1, OW = W >> 1;
+    const long total = (long)n * OH * OW;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int ox = (int)(idx % OW);
+    int oy = (int)((idx / OW) % OH);
+    int b = (int)(idx / ((long)OW * OH));
+    const uint8_t *__restrict__ base = run->input + (size_t)b * H * W * 3;
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; o++) acc[o] = sw[216 + o];
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+        int iy = oy * 2 + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+            int ix = ox * 2 + kx - 1;
+            if (ix < 0 || ix >= W) continue;
+            const uint8_t *p = base + ((size_t)iy * W + ix) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float v = (float)p[c];
+                const float *wr = &sw[((ky * 3 + kx) * 3 + c) * 8];
+#pragma unroll
+                for (int o = 0; o < 8; o++) acc[o] = fmaf(v, wr[o], acc[o]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; o++) acc[o] = fmaxf(acc[o], 0.f);
+    Vec8<T> v;
+    v.from_float(acc);
+    v.store(out + (size_t)idx * 8);
+}
+
+// ------------------------------------------------------------------------------------------
+// Depthwise 3x3 (+BN+ReLU): mobilenet0_conv{1,3,...,25} (prototxt:55 ...).  One thread per
+// (output pixel, 8-channel group); channels are the contiguous NHWC axis so a warp reads
+// 32 x 16 B (FP16) of consecutive channels/pixels.   wd: [9][C] floats, bias [C].
+// ------------------------------------------------------------------------------------------
+template <typename T, int STRIDE>
+__global__ void __launch_bounds__(256) k_dw3x3(const T *__restrict__ in, T *__restrict__ out,
+                                               const float *__restrict__ wd, const float *__restrict__ bias,
+                                               int n, int H, int W, int C) {
+    const int OH = H / STRIDE, OW = W / STRIDE;
+    const int cg = C >> 3;
+    const long total = (long)n * OH * OW * cg;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int g = (int)(idx % cg);
+    long pix = idx / cg;
+    int ox = (int)(pix % OW);
+    int oy = (int)((pix / OW) % OH);
+    int b = (int)(pix / ((long)OW * OH));
+    const int c0 = g * 8;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = __ldg(bias + c0 + i);
+    const T *base = in + (size_t)b * H * W * C + c0;
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+        int iy = oy * STRIDE + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+            int ix = ox * STRIDE + kx - 1;
+            if (ix < 0 || ix >= W) continue;
+            Vec8<T> v;
+            v.load(base + ((size_t)iy * W + ix) * C);
+            float f[8];
+            v.to_float(f);
+            const float *wr = wd + (ky * 3 + kx) * C + c0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = fmaf(f[i], __ldg(wr + i), acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = fmaxf(acc[i], 0.f);
+    Vec8<T> o;
+    o.from_float(acc);
+    o.store(out + (size_t)pix * C + c0);
+}
+
+// ------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution (1x1 or 3x3, stride 1, "same" padding) on CUDA cores:
+//   D[m][n] = sum_k A[m][k] * Wk[k][n] + bias[n],  m = output pixel, k = (tap, cin), n = cout.
+// Used for every pointwise conv (mobilenet0_conv{2,4,...,26}, rf_*_lateral / red_conv) and every
+// full 3x3 conv (rf_c*_aggr, the SSH det/context convs) in FP32 mode.
+// The epilogue can split the output channels over two destinations with their own pixel
+// stride / ReLU flag -- that is how the SSH branches write straight into the concat buffer
+// (prototxt:1418 Concat + :1427 ReLU) and how det_conv1 + context_conv1 share one launch.
+// Tile: 64 pixels x BN channels per CTA (256 threads: 16 pixel-threads x 16 channel-threads,
+// 4 x TN outputs each), K chunk 16.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct OutSplit {
+    T *p0; int ld0; int n0; int relu0;     // channels [0, n0)   -> p0[m*ld0 + n]
+    T *p1; int ld1; int relu1;             // channels [n0, N)   -> p1[m*ld1 + n - n0]
+};
+
+template <typename T, int BN, int KS>
+__global__ void __launch_bounds__(256) k_conv_gemm(const T *__restrict__ in, int ldin, int Cin,
+                                                   const float *__restrict__ wk, const float *__restrict__ bias,
+                                                   int N, OutSplit<T> outs, int nimg, int H, int W) {
+    constexpr int BM = 64, BK = 16, TN = BN / 16;
+    __shared__ float As[BK][BM + 2];
+    __shared__ float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long M = (long)nimg * H * W;
+    const long m0 = (long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    // A-load role: 4 threads per pixel, 4 consecutive channels each
+    const int lm = tid >> 2, lk = (tid & 3) * 4;
+    const long gm = m0 + lm;
+    int px = 0, py = 0, pb = 0;
+    const bool mvalid = gm < M;
+    if (mvalid) { px = (int)(gm % W); py = (int)((gm / W) % H); pb = (int)(gm / ((long)W * H)); }
+
+    float acc[4][TN];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+
+    const int kc = Cin < BK ? Cin : BK;  // channels per chunk (8 for the Cin=8 layer, else 16)
+    for (int tap = 0; tap < KS * KS; tap++) {
+        const int dy = KS == 3 ? tap / 3 - 1 : 0, dx = KS == 3 ? tap % 3 - 1 : 0;
+        const int iy = py + dy, ix = px + dx;
+        const bool inb = mvalid && iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const T *src = in + ((size_t)((size_t)pb * H + iy) * W + ix) * ldin;
+        for (int c0 = 0; c0 < Cin; c0 += kc) {
+            // A tile: As[k][m]
+            if (lk < kc) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (inb) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[i] = to_f(src[c0 + lk + i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) As[lk + i][lm] = v[i];
+            }
+            // B tile: Bs[k][n]
+            for (int i = tid; i < kc * BN; i += 256) {
+                int k = i / BN, nn = i % BN;
+                Bs[k][nn] = (n0 + nn < N) ? wk[(size_t)(tap * Cin + c0 + k) * N + n0 + nn] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int k = 0; k < kc; k++) {
+                float a[4], bv[TN];
+#pragma unroll
+                for (int i = 0; i < 4; i++) a[i] = As[k][ty + 16 * i];
+#pragma unroll
+                for (int j = 0; j < TN; j++) bv[j] = Bs[k][tx * TN + j];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        long m = m0 + ty + 16 * i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+            int nn = n0 + tx * TN + j;
+            if (nn >= N) continue;
+            float v = acc[i][j] + __ldg(bias + nn);
+            if (nn < outs.n0) {
+                if (outs.relu0) v = fmaxf(v, 0.f);
+                outs.p0[(size_t)m * outs.ld0 + nn] = from_f<T>(v);
+            } else {
+                if (outs.relu1) v = fmaxf(v, 0.f);
+                outs.p1[(size_t)m * outs.ld1 + (nn - outs.n0)] = from_f<T>(v);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FPN merge: out = lateral + crop(deconv_k4s2p1_depthwise(up))   (prototxt:1553-1592, 1948-1987)
+// Caffe Deconvolution: out[y] = sum_i in[i] * w[y - 2i + 1], out-of-range inputs contribute 0
+// (NOT a plain bilinear resize -- borders are attenuated).  The crop to
+// the lateral's H x W is the loop bound.  uw: [C][16] floats (the caffemodel's own kernel).
+// One thread per (output pixel, 8-channel group).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample_add(const T *__restrict__ lateral, const T *__restrict__ up,
+                                                      T *__restrict__ out, const float *__restrict__ uw,
+                                                      int n, int H, int W, int C, int UH, int UW) {
+    const int cg = C >> 3;
+    const long total = (long)n * H * W * cg;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int g = (int)(idx % cg);
+    long pix = idx / cg;
+    int x = (int)(pix % W);
+    int y = (int)((pix / W) % H);
+    int b = (int)(pix / ((long)W * H));
+    const int c0 = g * 8;
+    Vec8<T> lv;
+    lv.load(lateral + (size_t)pix * C + c0);
+    float acc[8];
+    lv.to_float(acc);
+    // contributing input rows: ky = y - 2i + 1 in [0,3]
+    const int i_hi = (y + 1) >> 1, j_hi = (x + 1) >> 1;
+#pragma unroll
+    for (int di = 0; di < 2; di++) {
+        int i = i_hi - di;
+        int ky = y - 2 * i + 1;
+        if (i < 0 || i >= UH || ky < 0 || ky > 3) continue;
+#pragma unroll
+        for (int dj = 0; dj < 2; dj++) {
+            int j = j_hi - dj;
+            int kx = x - 2 * j + 1;
+            if (j < 0 || j >= UW || kx < 0 || kx > 3) continue;
+            Vec8<T> uv;
+            uv.load(up + (((size_t)b * UH + i) * UW + j) * C + c0);
+            float f[8];
+            uv.to_float(f);
+#pragma unroll
+            for (int c = 0; c < 8; c++) acc[c] = fmaf(f[c], __ldg(uw + (c0 + c) * 16 + ky * 4 + kx), acc[c]);
+        }
+    }
+    Vec8<T> o;
+    o.from_float(acc);
+    o.store(out + (size_t)pix * C + c0);
+}
+
+}  // namespace rf

@@ -1,0 +1,346 @@
+// postproc.cu -- GPU post-process of librf_b200: predictor 1x1 convs + softmax + threshold +
+// anchor decode + clip (fused, all FPN levels in one launch) and sort + greedy NMS.
+//
+// Replaces the reference's HOST post-process, retinaface/RetinaFace.cpp:
+//   :666-687  blob gather (second half of cls_prob = P(face))         -> k_head_decode / k_blob_decode
+//   :689-723  threshold-first decode loop                              -> decode_one()
+//   :378-398  bbox_pred, :179-199 clip_boxes, :418-432 landmark_pred   -> decode_one()
+//   :127-154  anchors_plane (computed on the fly from (k, ih, iw))     -> decode_one()
+//   :434-492  CompareBBox sort + greedy nms                            -> k_nms
+// so that no head tensor (527 KB / image at 448x448) ever leaves the GPU.
+//
+// Bit-exactness contract: given identical head values, candidate selection, kept-face
+// selection and order are identical to the reference's; scores and landmarks are bit-identical;
+// box corners may differ by <= 1 ulp where the reference's expf (libm) is not correctly rounded
+// (we round exp() computed in double).  Every float operation below therefore spells its
+// rounding (__fmul_rn/__fadd_rn: no FMA contraction; the file is also built with -fmad=false),
+// and the `0.5 * (x - 1.0)` sub-expressions run in double like the reference's C++ does.
+// Ties in score (std::sort leaves them unspecified) are broken by emission order.
+#include "postproc.cuh"
+
+namespace rf {
+
+namespace {
+
+constexpr int NMS_THREADS = 512;
+constexpr int NMS_SMEM_CAP = 4096;  // candidates sorted / suppressed entirely in shared memory
+
+__device__ __forceinline__ unsigned long long make_key(float score, int emit) {
+    unsigned u = __float_as_uint(score);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving float -> uint
+    return ((unsigned long long)(~u) << 32) | (unsigned)emit;  // ascending key == score desc, emit asc
+}
+
+// One anchor: RetinaFace.cpp:695-721 (+ :127-154 anchor, :378-398, :179-199, :418-432).
+__device__ __forceinline__ void decode_one(float conf, const float reg[4], const float lmk[10],
+                                           const LevelDesc &lv, int num, int ih, int iw, int net_w, int net_h,
+                                           int emit, rf_det &d) {
+    // anchors_plane: base + (iw*stride, ih*stride)   (int -> float conversions are exact here)
+    const float sw = (float)(iw * lv.stride), sh = (float)(ih * lv.stride);
+    const float ax1 = __fadd_rn(lv.base[4 * num + 0], sw), ay1 = __fadd_rn(lv.base[4 * num + 1], sh);
+    const float ax2 = __fadd_rn(lv.base[4 * num + 2], sw), ay2 = __fadd_rn(lv.base[4 * num + 3], sh);
+    const float width = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f);
+    const float height = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
+    const float ctr_x = (float)((double)ax1 + 0.5 * ((double)width - 1.0));
+    const float ctr_y = (float)((double)ay1 + 0.5 * ((double)height - 1.0));
+    const float pcx = __fadd_rn(__fmul_rn(reg[0], width), ctr_x);
+    const float pcy = __fadd_rn(__fmul_rn(reg[1], height), ctr_y);
+    const float pw = __fmul_rn((float)exp((double)reg[2]), width);
+    const float ph = __fmul_rn((float)exp((double)reg[3]), height);
+    float x1 = (float)((double)pcx - 0.5 * ((double)pw - 1.0));
+    float y1 = (float)((double)pcy - 0.5 * ((double)ph - 1.0));
+    float x2 = (float)((double)pcx + 0.5 * ((double)pw - 1.0));
+    float y2 = (float)((double)pcy + 0.5 * ((double)ph - 1.0));
+    // clip_boxes (single): x1,y1 only lower-clamped, x2,y2 only upper-clamped
+    if (x1 < 0) x1 = 0;
+    if (y1 < 0) y1 = 0;
+    if (x2 > (float)(net_w - 1)) x2 = (float)(net_w - 1);
+    if (y2 > (float)(net_h - 1)) y2 = (float)(net_h - 1);
+    d.face.score = conf;
+    d.face.x1 = x1; d.face.y1 = y1; d.face.x2 = x2; d.face.y2 = y2;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        d.face.lx[k] = __fadd_rn(__fmul_rn(lmk[2 * k], width), ctr_x);
+        d.face.ly[k] = __fadd_rn(__fmul_rn(lmk[2 * k + 1], height), ctr_y);
+    }
+    d.anchor_index = emit;
+}
+
+__device__ __forceinline__ void append_candidate(const PostBuffers &pb, int img, const rf_det &d) {
+    const size_t base = (size_t)img * pb.anchors_per_image;
+    pb.cand_recs[base + d.anchor_index] = d;
+    int slot = atomicAdd(&pb.cand_count[img], 1);
+    if (slot < pb.anchors_per_image) pb.cand_keys[base + slot] = make_key(d.face.score, d.anchor_index);
+}
+
+struct HeadLaunch {
+    const void *feat[3];
+    HeadWeights hw[3];
+    LevelDesc lv[3];
+    int blk_base[4];   // first block of each level (level-aligned blocks)
+    float *blobs[9];
+};
+
+// One thread per feature-map pixel; a block never straddles levels so its shared memory holds
+// exactly one level's 32x64 predictor weights.
+template <typename T, bool WRITE_BLOBS>
+__global__ void __launch_bounds__(128) k_head_decode(HeadLaunch L, int net_w, int net_h,
+                                                     const PostParams *__restrict__ params, PostBuffers pb) {
+    __shared__ __align__(16) float sw[32 * 64];
+    __shared__ float sb[32];
+    const int blk = blockIdx.x;
+    const int l = blk >= L.blk_base[2] ? 2 : (blk >= L.blk_base[1] ? 1 : 0);
+    const LevelDesc lv = L.lv[l];
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) sw[i] = L.hw[l].w[i];
+    if (threadIdx.x < 32) sb[threadIdx.x] = L.hw[l].b[threadIdx.x];
+    __syncthreads();
+    const int hw = lv.h * lv.w;
+    const int j = (blk - L.blk_base[l]) * blockDim.x + threadIdx.x;
+    if (j >= hw) return;
+    const int img = blockIdx.y;
+    const float thr = params->score_thr;
+    const T *f = reinterpret_cast<const T *>(L.feat[l]) + ((size_t)img * hw + j) * 64;
+    float x[64];
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+        Vec8<T> v;
+        v.load(f + g * 8);
+        v.to_float(&x[g * 8]);
+    }
+    auto dot = [&](int o) -> float {
+        float acc = sb[o];
+        const float4 *w4 = reinterpret_cast<const float4 *>(&sw[o * 64]);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            float4 w = w4[c];
+            acc = __fmaf_rn(x[4 * c + 0], w.x, acc);
+            acc = __fmaf_rn(x[4 * c + 1], w.y, acc);
+            acc = __fmaf_rn(x[4 * c + 2], w.z, acc);
+            acc = __fmaf_rn(x[4 * c + 3], w.w, acc);
+        }
+        return acc;
+    };
+    float s[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++) s[o] = dot(o);
+    // Softmax over the (N,2,2h,w) view (prototxt:1448-1483): anchor a pairs channel a (bg) with a+2 (face).
+    float pf[2], pbg[2];
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+        float m = fmaxf(s[a], s[a + 2]);
+        float e0 = expf(__fsub_rn(s[a], m)), e1 = expf(__fsub_rn(s[a + 2], m));
+        float sum = __fadd_rn(e0, e1);
+        pbg[a] = __fdiv_rn(e0, sum);
+        pf[a] = __fdiv_rn(e1, sum);
+    }
+    const int ih = j / lv.w, iw = j % lv.w;
+    if (WRITE_BLOBS) {
+        float *cls = L.blobs[3 * l] + (size_t)img * 4 * hw;
+        cls[0 * hw + j] = pbg[0]; cls[1 * hw + j] = pbg[1]; cls[2 * hw + j] = pf[0]; cls[3 * hw + j] = pf[1];
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+        const bool pass = !(pf[a] <= thr);   // reference: `if (conf <= threshold) continue;`
+        if (!pass && !WRITE_BLOBS) continue;
+        float reg[4], lm[10];
+#pragma unroll
+        for (int c = 0; c < 4; c++) reg[c] = dot(4 + a * 4 + c);
+#pragma unroll
+        for (int c = 0; c < 10; c++) lm[c] = dot(12 + a * 10 + c);
+        if (WRITE_BLOBS) {
+            float *bb = L.blobs[3 * l + 1] + (size_t)img * 8 * hw;
+            float *lb = L.blobs[3 * l + 2] + (size_t)img * 20 * hw;
+#pragma unroll
+            for (int c = 0; c < 4; c++) bb[(a * 4 + c) * hw + j] = reg[c];
+#pragma unroll
+            for (int c = 0; c < 10; c++) lb[(a * 10 + c) * hw + j] = lm[c];
+        }
+        if (pass) {
+            rf_det d;
+            decode_one(pf[a], reg, lm, lv, a, ih, iw, net_w, net_h, lv.anchor_base + a * hw + j, d);
+            append_candidate(pb, img, d);
+        }
+    }
+}
+
+struct BlobLaunch {
+    const float *blobs[9];
+    LevelDesc lv[3];
+};
+
+// rf_postprocess: one thread per anchor, reading caller-supplied NCHW head blobs.
+__global__ void __launch_bounds__(256) k_blob_decode(BlobLaunch L, int net_w, int net_h,
+                                                     const PostParams *__restrict__ params, PostBuffers pb) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;  // emission index within the image
+    if (e >= pb.anchors_per_image) return;
+    const int img = blockIdx.y;
+    const int l = e >= L.lv[2].anchor_base ? 2 : (e >= L.lv[1].anchor_base ? 1 : 0);
+    const LevelDesc lv = L.lv[l];
+    const int hw = lv.h * lv.w;
+    const int r = e - lv.anchor_base;
+    const int num = r / hw, j = r % hw;
+    const float *cls = L.blobs[3 * l] + (size_t)img * 4 * hw;
+    const float conf = cls[(2 + num) * hw + j];
+    if (conf <= params->score_thr) return;
+    const float *bb = L.blobs[3 * l + 1] + (size_t)img * 8 * hw;
+    const float *lb = L.blobs[3 * l + 2] + (size_t)img * 20 * hw;
+    float reg[4], lm[10];
+#pragma unroll
+    for (int c = 0; c < 4; c++) reg[c] = bb[(num * 4 + c) * hw + j];
+#pragma unroll
+    for (int c = 0; c < 10; c++) lm[c] = lb[(num * 10 + c) * hw + j];
+    rf_det d;
+    decode_one(conf, reg, lm, lv, num, j / lv.w, j % lv.w, net_w, net_h, e, d);
+    append_candidate(pb, img, d);
+}
+
+// IoU test of RetinaFace::nms (:470-487), operation by operation.
+__device__ __forceinline__ bool suppresses(const float4 s, float area1, const float4 b, float thr) {
+    float x = fmaxf(s.x, b.x), y = fmaxf(s.y, b.y);
+    float w = __fadd_rn(__fsub_rn(fminf(s.z, b.z), x), 1.0f);
+    float h = __fadd_rn(__fsub_rn(fminf(s.w, b.w), y), 1.0f);
+    if (w <= 0 || h <= 0) return false;
+    float area2 = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+    float inter = __fmul_rn(w, h);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area1, area2), inter)) > thr;
+}
+
+// One CTA per image.  (1) bitonic sort of the candidate keys, (2) greedy suppression rounds: the
+// next unsuppressed candidate is kept, then all threads test the remaining ones against it --
+// the same O(n * kept) work as the reference, parallel inside a round, (3) gather kept records.
+__global__ void __launch_bounds__(NMS_THREADS) k_nms(const PostParams *__restrict__ params, PostBuffers pb) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int img = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int A = pb.anchors_per_image;
+    int n = pb.cand_count[img];
+    if (n > A) n = A;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    const bool small = np2 <= NMS_SMEM_CAP;
+    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem);
+    float4 *s_box = reinterpret_cast<float4 *>(smem + sizeof(unsigned long long) * NMS_SMEM_CAP);
+    unsigned char *s_flag = smem + (sizeof(unsigned long long) + sizeof(float4)) * NMS_SMEM_CAP;
+    int *s_kept = reinterpret_cast<int *>(s_flag + NMS_SMEM_CAP);
+    __shared__ int s_nkept;
+
+    unsigned long long *keys = small ? s_keys : pb.sort_scratch + (size_t)img * pb.anchors_pow2;
+    unsigned char *flag = small ? s_flag : pb.flag_scratch + (size_t)img * pb.anchors_pow2;
+    const unsigned long long *gkeys = pb.cand_keys + (size_t)img * A;
+    const rf_det *recs = pb.cand_recs + (size_t)img * A;
+
+    for (int i = tid; i < np2; i += NMS_THREADS) {
+        keys[i] = i < n ? gkeys[i] : ~0ull;
+        flag[i] = 0;
+    }
+    if (tid == 0) s_nkept = 0;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += NMS_THREADS) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = keys[i], b = keys[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (small) {
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const rf_face &f = recs[(unsigned)(keys[i] & 0xffffffffu)].face;
+            s_box[i] = make_float4(f.x1, f.y1, f.x2, f.y2);
+        }
+        __syncthreads();
+    }
+    const float thr = params->nms_thr;
+    auto box_at = [&](int i) -> float4 {
+        if (small) return s_box[i];
+        const rf_face &f = recs[(unsigned)(keys[i] & 0xffffffffu)].face;
+        return make_float4(f.x1, f.y1, f.x2, f.y2);
+    };
+    int nkept = 0;  // thread 0's running count (mirrored to s_nkept at the end)
+    for (int i = 0; i < n; i++) {
+        if (flag[i]) continue;  // uniform: flags of position i are final (see header comment)
+        const float4 s = box_at(i);
+        if (tid == 0) {
+            if (nkept < pb.max_faces) s_kept[nkept] = i;
+            nkept++;
+        }
+        const float area1 = __fmul_rn(__fadd_rn(__fsub_rn(s.z, s.x), 1.0f), __fadd_rn(__fsub_rn(s.w, s.y), 1.0f));
+        for (int j = i + 1 + tid; j < n; j += NMS_THREADS) {
+            if (!flag[j] && suppresses(s, area1, box_at(j), thr)) flag[j] = 1;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) s_nkept = nkept;
+    __syncthreads();
+    const int total = s_nkept;
+    const int kept = total < pb.max_faces ? total : pb.max_faces;
+    // gather: 16 floats per record, one thread per float
+    const float *src = reinterpret_cast<const float *>(recs);
+    float *dst = reinterpret_cast<float *>(pb.out_dets + (size_t)img * pb.max_faces);
+    for (int t = tid; t < kept * 16; t += NMS_THREADS) {
+        int k = t >> 4, w = t & 15;
+        unsigned e = (unsigned)(keys[s_kept[k]] & 0xffffffffu);
+        dst[t] = src[(size_t)e * 16 + w];
+    }
+    if (tid == 0) {
+        pb.out_counts[img] = kept;
+        pb.out_total_kept[img] = total;
+        pb.cand_count[img] = 0;  // self-cleaning for the next launch
+    }
+}
+
+size_t nms_smem_bytes(int max_faces) {
+    return (sizeof(unsigned long long) + sizeof(float4) + 1) * (size_t)NMS_SMEM_CAP + sizeof(int) * (size_t)max_faces;
+}
+
+}  // namespace
+
+template <typename T>
+void launch_head_decode(const T *const feat[3], const HeadWeights hw[3], const LevelDesc lv[3], int n,
+                        int net_w, int net_h, const PostParams *params, const PostBuffers &pb,
+                        float *const blobs[9], cudaStream_t s) {
+    HeadLaunch L;
+    int blk = 0;
+    bool write = blobs && blobs[0];
+    for (int l = 0; l < 3; l++) {
+        L.feat[l] = feat[l];
+        L.hw[l] = hw[l];
+        L.lv[l] = lv[l];
+        L.blk_base[l] = blk;
+        blk += (lv[l].h * lv[l].w + 127) / 128;
+    }
+    L.blk_base[3] = blk;
+    for (int i = 0; i < 9; i++) L.blobs[i] = write ? blobs[i] : nullptr;
+    dim3 grid(blk, n);
+    if (write) k_head_decode<T, true><<<grid, 128, 0, s>>>(L, net_w, net_h, params, pb);
+    else k_head_decode<T, false><<<grid, 128, 0, s>>>(L, net_w, net_h, params, pb);
+}
+template void launch_head_decode<float>(const float *const[3], const HeadWeights[3], const LevelDesc[3], int, int, int,
+                                        const PostParams *, const PostBuffers &, float *const[9], cudaStream_t);
+template void launch_head_decode<__half>(const __half *const[3], const HeadWeights[3], const LevelDesc[3], int, int, int,
+                                         const PostParams *, const PostBuffers &, float *const[9], cudaStream_t);
+
+void launch_blob_decode(const float *const blobs[9], const LevelDesc lv[3], int n, int net_w, int net_h,
+                        const PostParams *params, const PostBuffers &pb, cudaStream_t s) {
+    BlobLaunch L;
+    for (int i = 0; i < 9; i++) L.blobs[i] = blobs[i];
+    for (int l = 0; l < 3; l++) L.lv[l] = lv[l];
+    dim3 grid((pb.anchors_per_image + 255) / 256, n);
+    k_blob_decode<<<grid, 256, 0, s>>>(L, net_w, net_h, params, pb);
+}
+
+void launch_nms(int n, const PostParams *params, const PostBuffers &pb, cudaStream_t s) {
+    k_nms<<<n, NMS_THREADS, nms_smem_bytes(pb.max_faces), s>>>(params, pb);
+}
+
+cudaError_t postproc_init() {
+    // worst case max_faces is bounded by the engine (<= 8192): reserve for that
+    return cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes(8192));
+}
+
+}  // namespace rf

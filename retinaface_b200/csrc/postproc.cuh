@@ -1,0 +1,46 @@
+// postproc.cuh -- launch wrappers of the GPU post-process (implemented in postproc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace rf {
+
+struct PostBuffers {
+    // per image i (capacity = anchors_per_image A):
+    unsigned long long *cand_keys;  // [B][A]   sort keys of candidates in append order
+    rf_det *cand_recs;              // [B][A]   decoded record, indexed by anchor emission index
+    int *cand_count;                // [B]      number appended (reset by the head kernel's launch wrapper)
+    unsigned long long *sort_scratch;  // [B][A_pow2] global scratch for sorts that do not fit in smem
+    unsigned char *flag_scratch;    // [B][A_pow2]
+    rf_det *out_dets;               // [B][max_faces]
+    int *out_counts;                // [B]   kept (clamped to max_faces)
+    int *out_total_kept;            // [B]   kept before clamping
+    int anchors_per_image;
+    int anchors_pow2;
+    int max_faces;
+};
+
+struct HeadWeights {
+    const float *w;     // [32][64]: rows 0-3 cls_score, 4-11 bbox_pred, 12-31 landmark_pred
+    const float *b;     // [32]
+};
+
+// Fused per-level predictor + decode: 1x1 convs (cls 4, bbox 8, landmark 20), the 2-way softmax,
+// threshold, anchor decode, clip -> candidate append.  One launch covers all three levels.
+// feat[l]: NHWC [n][h][w][64] SSH output (post concat+ReLU) in T.  blobs (optional, may be all
+// NULL): the 9 NCHW float32 head blobs in engine order, for rf_forward_heads.
+template <typename T>
+void launch_head_decode(const T *const feat[3], const HeadWeights hw[3], const LevelDesc lv[3], int n,
+                        int net_w, int net_h, const PostParams *params, const PostBuffers &pb,
+                        float *const blobs[9], cudaStream_t s);
+
+// Decode from caller-provided head blobs (device, NCHW f32, engine order): rf_postprocess.
+void launch_blob_decode(const float *const blobs[9], const LevelDesc lv[3], int n, int net_w, int net_h,
+                        const PostParams *params, const PostBuffers &pb, cudaStream_t s);
+
+// Sort candidates by (score desc, emission index asc) and run greedy NMS; one CTA per image.
+void launch_nms(int n, const PostParams *params, const PostBuffers &pb, cudaStream_t s);
+
+// dynamic shared memory the NMS kernel wants (set once at init)
+cudaError_t postproc_init();
+
+}  // namespace rf

@@ -1,0 +1,260 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the oracle and the
+committed golden fixtures.  Tolerances are written next to each assertion.
+
+Nothing here reads /root/reference (absent on the GPU box): golden fixtures + the oracle only.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, caffemodel
+from oracle import topology
+from oracle.inputs import letterbox_bgr_u8, s_noise_batch, s_real_batch
+from oracle.mnet_numpy import MnetOracle, preprocess_bgr_u8
+from oracle.postproc import PostprocOracle, ReferencePostproc, synth_heads
+
+pytestmark = pytest.mark.gpu
+
+# FP32 mode: same math as the oracle up to summation order -> observed ~1e-5; gate at 2e-4 abs.
+TOL_FP32 = 2e-4
+
+
+def _engine(model, h, w, prec, **kw):
+    from retinaface_b200 import Engine
+    return Engine(caffemodel(model), h, w, precision=prec, **kw)
+
+
+def _compare_dets(mine, mine_idx, ref, label=""):
+    """Selection (anchor emission indices, order) bit-exact; scores + landmarks bit-exact; box corners
+    within 4e-6 relative (the exp() rounding noted in postproc.cu)."""
+    assert mine_idx.tolist() == ref["idx"].tolist(), label
+    a, b = mine, ref["faces"]
+    assert a.shape == b.shape, label
+    if len(a) == 0:
+        return
+    assert np.array_equal(a[:, 0], b[:, 0]), label            # scores
+    assert np.array_equal(a[:, 5:], b[:, 5:]), label          # landmarks
+    assert np.allclose(a[:, 1:5], b[:, 1:5], rtol=4e-6, atol=1e-4), label
+
+
+@pytest.fixture(scope="module")
+def post_oracle():
+    return PostprocOracle()
+
+
+@pytest.mark.parametrize("hw", [(448, 448), (896, 1280)])
+def test_postprocess_kernels_vs_oracle(post_oracle, hw):
+    """rf_postprocess (decode + threshold + sort + NMS kernels) on synthetic S-nms head tensors."""
+    from retinaface_b200 import RF_PREC_FP32
+    h, w = hw
+    eng = _engine("mnet25", h, w, RF_PREC_FP32, max_batch=4, max_faces=8192)
+    try:
+        for ncand in (0, 1, 37, 64, 1024, 4000, 8192):
+            batch = [synth_heads(h, w, ncand, seed=100 + ncand + i) for i in range(3)]
+            heads = [np.stack([b[k] for b in batch]) for k in range(9)]
+            for thr, nms in ((0.9, 0.4), (0.5, 0.4), (0.9, 0.0), (0.9, 1.0)):
+                if ncand > 1024 and (thr, nms) != (0.9, 0.4):
+                    continue
+                faces, idx, ncands = eng.postprocess(heads, thr, nms)
+                for i in range(3):
+                    ref = post_oracle.postprocess(batch[i], h, w, thr, nms)
+                    assert ncands[i] == len(ref["cand"]), (ncand, thr, nms, i)
+                    _compare_dets(faces[i], idx[i], ref, f"ncand={ncand} thr={thr} nms={nms} img={i}")
+    finally:
+        eng.close()
+
+
+def test_postprocess_matches_reference_compiled_code():
+    """Same, against oracle/_ref (the reference's own RetinaFace::postProcess), when it travelled here."""
+    if not ReferencePostproc.available():
+        pytest.skip("oracle/_ref/libref_postproc.so not present")
+    from retinaface_b200 import RF_PREC_FP32
+    h = w = 448
+    eng = _engine("mnet25", h, w, RF_PREC_FP32, max_batch=1, max_faces=4096)
+    ref = ReferencePostproc(h, w)
+    try:
+        for ncand in (5, 300, 2000):
+            heads = synth_heads(h, w, ncand, seed=7 + ncand)
+            faces, idx, _ = eng.postprocess([x[None] for x in heads], 0.9, 0.4)
+            theirs = ref.postprocess(heads, 0.9)
+            assert faces[0].shape == theirs.shape
+            assert np.array_equal(faces[0][:, 0], theirs[:, 0])
+            assert np.array_equal(faces[0][:, 5:], theirs[:, 5:])
+            assert np.allclose(faces[0][:, 1:5], theirs[:, 1:5], rtol=4e-6, atol=1e-4)
+    finally:
+        ref.close()
+        eng.close()
+
+
+def test_postprocess_edge_cases(post_oracle):
+    from retinaface_b200 import RF_PREC_FP32
+    h = w = 64
+    eng = _engine("mnet25", h, w, RF_PREC_FP32, max_batch=2, max_faces=512)
+    try:
+        # every anchor a candidate (168 of them), strict threshold, ties broken by emission order
+        heads = synth_heads(h, w, 10_000)
+        faces, idx, nc = eng.postprocess([x[None] for x in heads], 0.9, 0.4)
+        ref = post_oracle.postprocess(heads, h, w, 0.9, 0.4)
+        assert nc[0] == 168
+        _compare_dets(faces[0], idx[0], ref)
+        z = synth_heads(h, w, 0)
+        z[0][2, 0, 0] = np.float32(0.9)
+        assert eng.postprocess([x[None] for x in z], 0.9, 0.4)[2][0] == 0          # conf == thr dropped
+        z[6][2, 0, 0] = 0.95
+        z[0][2, 1, 1] = 0.95
+        faces, idx, nc = eng.postprocess([x[None] for x in z], 0.9, 1.0)
+        assert nc[0] == 2 and idx[0].tolist() == sorted(idx[0].tolist())
+        # max_faces clamp keeps the top-scoring ones
+        small = _engine("mnet25", h, w, RF_PREC_FP32, max_batch=1, max_faces=4)
+        f2, i2, _ = small.postprocess([x[None] for x in heads], 0.9, 0.4)
+        assert len(f2[0]) == 4 and np.array_equal(f2[0], faces_all(eng, heads)[:4])
+        small.close()
+    finally:
+        eng.close()
+
+
+def faces_all(eng, heads):
+    return eng.postprocess([x[None] for x in heads], 0.9, 0.4)[0][0]
+
+
+@pytest.mark.parametrize("model", ["mnet-deconv-0517", "mnet25"])
+def test_fp32_forward_heads_vs_golden_and_oracle(model, golden_image):
+    """FP32 CUDA forward vs (a) golden head blobs frozen from cv2.dnn on the reference's own model
+    files, (b) the numpy oracle on seeded noise; plus every intermediate activation."""
+    from retinaface_b200 import RF_PREC_FP32
+    eng = _engine(model, 448, 448, RF_PREC_FP32, max_batch=2)
+    try:
+        eng.debug_keep_all()
+        inp = letterbox_bgr_u8(golden_image, 448, 448)
+        noise = s_noise_batch(1, 448, 448, seed=0)[0]
+        batch = np.stack([inp, noise])
+        heads = eng.forward_heads(batch)
+        gold = np.load(os.path.join(GOLDEN, f"heads_{model}_448.npz"))
+        for k, name in enumerate(topology.OUTPUT_BLOBS):
+            err = np.abs(heads[k][0] - gold[name]).max()
+            assert err < TOL_FP32, (name, err)
+        orc = MnetOracle(caffemodel(model))
+        inter = ["mobilenet0_relu0_fwd", "mobilenet0_relu1_fwd", "mobilenet0_relu2_fwd", "mobilenet0_relu10_fwd",
+                 "mobilenet0_relu22_fwd", "mobilenet0_relu26_fwd", "rf_c3_lateral_relu", "_plus0", "rf_c2_aggr_relu",
+                 "_plus1", "rf_c1_aggr_relu", "rf_c3_det_concat_relu", "rf_c2_det_concat_relu", "rf_c1_det_concat_relu"]
+        x = np.concatenate([preprocess_bgr_u8(inp), preprocess_bgr_u8(noise)])
+        ref = orc.forward(x, want=list(topology.OUTPUT_BLOBS) + inter)
+        for name in inter:
+            got = eng.debug_tensor(name, 2)
+            scale = max(1.0, float(np.abs(ref[name]).max()))
+            err = np.abs(got - ref[name]).max() / scale
+            assert err < TOL_FP32, (name, err)
+        for k, name in enumerate(topology.OUTPUT_BLOBS):
+            err = np.abs(heads[k] - ref[name]).max()
+            assert err < TOL_FP32, (name, err)
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("hw", [(448, 448), (896, 1280)])
+def test_fp32_detect_matches_golden_detections(hw, golden_image, post_oracle):
+    """End to end through rf_detect_batch (host images in, faces out) against the detections frozen
+    from the reference's own post-process on cv2.dnn heads: same faces, same order; coordinates within
+    2e-3 px (FP32 conv summation order), scores within 1e-5."""
+    from retinaface_b200 import RF_PREC_FP32
+    h, w = hw
+    for model in ("mnet-deconv-0517", "mnet25"):
+        eng = _engine(model, h, w, RF_PREC_FP32, max_batch=2, max_image=(1024, 1536))
+        try:
+            dets = np.load(os.path.join(GOLDEN, f"dets_{model}_{h}x{w}.npz"))
+            inp = letterbox_bgr_u8(golden_image, h, w)
+            for thr in (0.9, 0.5):
+                faces, idx = eng.detect_batch([inp, inp], thr, 0.4, want_index=True)
+                g = dets[f"faces_thr{thr}"]
+                for f in faces:
+                    assert f.shape == g.shape, (model, hw, thr, f.shape, g.shape)
+                    assert np.abs(f[:, 0] - g[:, 0]).max() < 1e-5
+                    assert np.abs(f[:, 1:] - g[:, 1:]).max() < 2e-3
+                assert np.array_equal(faces[0], faces[1])
+            # consistency: rf_forward_heads -> oracle post-process == rf_detect_batch, selection bit-exact
+            heads = eng.forward_heads(inp[None])
+            ref = post_oracle.postprocess([x[0] for x in heads], h, w, 0.5, 0.4)
+            faces, idx = eng.detect_batch([inp], 0.5, 0.4, want_index=True)
+            _compare_dets(faces[0], idx[0], ref, f"{model} {hw}")
+            if hw == (448, 448):
+                # the un-letterboxed 1280x886 photo through the GPU letterbox kernel: same result
+                f2 = eng.detect_batch([golden_image], 0.5, 0.4)
+                assert np.array_equal(f2[0], faces[0])
+        finally:
+            eng.close()
+
+
+def test_preprocess_letterbox_bit_exact(golden_image):
+    """rf_preprocess (GPU letterbox kernel) vs the oracle's cv2.resize-based letterbox: identical bytes."""
+    from retinaface_b200 import RF_PREC_FP32
+    rng = np.random.default_rng(5)
+    eng = _engine("mnet25", 448, 448, RF_PREC_FP32, max_batch=1, max_image=(2048, 2048))
+    try:
+        cases = [golden_image, rng.integers(0, 256, (333, 517, 3), dtype=np.uint8), rng.integers(0, 256, (900, 700, 3), dtype=np.uint8),
+                 rng.integers(0, 256, (896, 896, 3), dtype=np.uint8), rng.integers(0, 256, (100, 448, 3), dtype=np.uint8),
+                 rng.integers(0, 256, (448, 448, 3), dtype=np.uint8), rng.integers(0, 256, (2000, 31, 3), dtype=np.uint8),
+                 rng.integers(0, 256, (1, 1, 3), dtype=np.uint8)]
+        for img in cases:
+            assert np.array_equal(eng.preprocess(img), letterbox_bgr_u8(img, 448, 448)), img.shape
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("model", ["mnet25", "mnet-deconv-0517"])
+def test_fp16_forward_and_detect(model, golden_image, post_oracle):
+    """FP16 path (configs[1]): head tensors vs golden FP32 heads within FP16 tolerance
+    (cls_prob abs 5e-3, deltas abs 1e-2), detections on the golden image: same faces as the
+    FP32 golden ones, boxes within 0.5 px, scores within 5e-3; and internal consistency
+    (its own heads -> oracle post-process == its own detect) bit-exact in selection."""
+    from retinaface_b200 import RF_PREC_FP16
+    eng = _engine(model, 448, 448, RF_PREC_FP16, max_batch=8)
+    try:
+        inp = letterbox_bgr_u8(golden_image, 448, 448)
+        batch = s_real_batch(inp, 8)
+        heads = eng.forward_heads(batch)
+        gold = np.load(os.path.join(GOLDEN, f"heads_{model}_448.npz"))
+        for k, name in enumerate(topology.OUTPUT_BLOBS):
+            err = np.abs(heads[k][0] - gold[name]).max()
+            assert err < (5e-3 if "cls_prob" in name else 1e-2), (name, err)
+        dets = np.load(os.path.join(GOLDEN, f"dets_{model}_448x448.npz"))["faces_thr0.9"]
+        faces, idx = eng.detect_batch(list(batch), 0.9, 0.4, want_index=True)
+        assert faces[0].shape == dets.shape
+        assert np.abs(faces[0][:, 0] - dets[:, 0]).max() < 5e-3
+        assert np.abs(faces[0][:, 1:] - dets[:, 1:]).max() < 0.5
+        for i in range(8):
+            ref = post_oracle.postprocess([x[i] for x in heads], 448, 448, 0.9, 0.4)
+            _compare_dets(faces[i], idx[i], ref, f"fp16 img {i}")
+            assert len(faces[i]) >= 4
+    finally:
+        eng.close()
+
+
+def test_graph_replay_equals_direct_launch(golden_image):
+    from retinaface_b200 import RF_PREC_FP16
+    from retinaface_b200.capi import RF_FLAG_NO_GRAPH
+    inp = letterbox_bgr_u8(golden_image, 448, 448)
+    batch = list(s_real_batch(inp, 5))
+    a = _engine("mnet25", 448, 448, RF_PREC_FP16, max_batch=8)
+    b = _engine("mnet25", 448, 448, RF_PREC_FP16, max_batch=8, flags=RF_FLAG_NO_GRAPH)
+    try:
+        for _ in range(3):  # replay several times, varying batch size
+            for n in (5, 1, 3):
+                fa = a.detect_batch(batch[:n], 0.9, 0.4)
+                fb = b.detect_batch(batch[:n], 0.9, 0.4)
+                for x, y in zip(fa, fb):
+                    assert np.array_equal(x, y)
+    finally:
+        a.close()
+        b.close()
+
+
+def test_detector_class_mirror(golden_image):
+    """RetinaFace(model_dir, "net3").detect(img, 0.9) -- the call main.cpp:15,43 makes."""
+    from retinaface_b200 import RetinaFace
+    rf = RetinaFace(os.path.join(GOLDEN, "weights"), "net3", net_w=448, net_h=448)
+    faces = rf.detect(golden_image, 0.9)
+    assert len(faces) == 5 and abs(faces[0].score - 0.9986) < 5e-3
+    assert rf.detect(np.zeros((0, 0, 3), np.uint8), 0.9) == []
+    per = rf.detectBatchImages([golden_image, golden_image[:400, :600]], 0.9)
+    assert len(per) == 2 and len(per[0]) == 5

@@ -1,0 +1,73 @@
+"""CPU: the C-ABI library loads, exports every declared symbol, and its host-side logic (model
+front end, argument validation, error reporting) behaves -- no compute calls without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, caffemodel
+
+
+def test_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "rf_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(rf_[a-z0-9_]+)\s*\(", hdr)) - {"rf_handle_s"})
+    from retinaface_b200 import capi
+    assert sorted(capi.EXPORTS) == declared
+    lib = C.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.rf_abi_version() == 1
+
+
+def test_product_has_no_oracle_dependency():
+    """The product package must not import or link anything under oracle/ (nor any CPU fallback)."""
+    pkg = os.path.join(ROOT, "retinaface_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(root, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "liboracle" not in src and "oracle/" not in src.replace("oracle/__init__", ""), f
+
+
+def test_model_front_end_matches_oracle_fold(built_lib):
+    from oracle.mnet_numpy import folded_params
+    from retinaface_b200.capi import model_inspect
+    for m in ("mnet25", "mnet-deconv-0517"):
+        fp = folded_params(caffemodel(m))
+        n = 0
+        for name, d in fp.items():
+            if "b" not in d:
+                continue
+            w, b = model_inspect(caffemodel(m), name)
+            assert np.array_equal(w, d["w"]) and np.array_equal(b, d["b"]), name
+            n += 1
+        assert n == 27 + 5 + 15 + 9
+
+
+def test_error_paths_without_gpu(built_lib, tmp_path):
+    from retinaface_b200 import Engine, RfError
+    with pytest.raises(RfError) as e:
+        Engine(str(tmp_path / "missing.caffemodel"), 448, 448)
+    assert e.value.status == -2
+    bad = tmp_path / "bad.caffemodel"
+    bad.write_bytes(b"\x0a\x03abc")  # a NetParameter with only a name
+    with pytest.raises(RfError) as e:
+        Engine(str(bad), 448, 448)
+    assert e.value.status == -3
+    with pytest.raises(RfError) as e:
+        Engine(caffemodel("mnet25"), 450, 448)  # not a multiple of 32
+    assert e.value.status == -1
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RfError) as e:
+            Engine(caffemodel("mnet25"), 448, 448)
+        assert e.value.status == -5 and "no CPU path" in str(e.value)
+
+
+def test_detector_mirror_rejects_unconfigured_networks(built_lib):
+    from retinaface_b200 import RetinaFace
+    with pytest.raises(ValueError):
+        RetinaFace("tests/golden/weights", "net5")
