@@ -12,6 +12,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -19,6 +20,7 @@
 #include "model.h"
 #include "postproc.cuh"
 #include "preprocess.cuh"
+#include "tc_conv.cuh"
 
 using namespace rf;
 
@@ -83,6 +85,9 @@ struct rf_handle_s {
     // weights
     std::vector<float> wstage;  // host staging of all fp32 weights
     float *d_weights = nullptr;
+    std::vector<__half> wstage_h;  // FP16 tensor-core weight images (tc_conv.cuh B chunks)
+    __half *d_weights_h = nullptr;
+    bool use_tc = false;
 
     // io
     uint8_t *d_input = nullptr;       // [max_batch][H][W][3] u8 BGR
@@ -130,6 +135,12 @@ struct Builder {
         while (h->wstage.size() % 4) h->wstage.push_back(0.f);  // keep float4 alignment
         return off;
     }
+    size_t add_weights_h(const std::vector<__half> &v) {
+        size_t off = h->wstage_h.size();
+        h->wstage_h.insert(h->wstage_h.end(), v.begin(), v.end());
+        while (h->wstage_h.size() % 64) h->wstage_h.push_back(__float2half(0.f));  // 128-byte alignment for bulk copies
+        return off;
+    }
     int tensor(const std::string &name, int hh, int ww, int c) {
         TensorInfo t;
         t.name = name; t.h = hh; t.w = ww; t.c = c;
@@ -175,6 +186,63 @@ void launch_gemm(const T *in, int ldin, int cin, const float *wk, const float *b
 #undef RF_GEMM
 }
 
+// ---- tcgen05 path helpers --------------------------------------------------------------------
+// B operand images: per 64-wide K chunk, [k/8][n][8] halfs (the UMMA K-major no-swizzle layout of
+// tc_conv.cuh), K ordered (tap, cin); convs sharing an input are concatenated along N.
+std::vector<__half> pack_tc_weights(const std::vector<const FoldedConv *> &cs, std::vector<float> &bias, int &Kpad) {
+    const int cin = cs[0]->cin, k = cs[0]->k;
+    int N = 0;
+    for (auto c : cs) N += c->cout;
+    const int K = k * k * cin;
+    Kpad = (K + 15) / 16 * 16;
+    const int nch = (Kpad + TC_KC - 1) / TC_KC;
+    std::vector<__half> img((size_t)nch * N * TC_KC, __float2half(0.f));
+    bias.assign(N, 0.f);
+    int n0 = 0;
+    for (auto c : cs) {
+        for (int o = 0; o < c->cout; o++) {
+            bias[n0 + o] = c->b[o];
+            for (int ci = 0; ci < cin; ci++)
+                for (int t = 0; t < k * k; t++) {
+                    int kk = t * cin + ci, q = kk / TC_KC, kl = kk % TC_KC;
+                    img[(size_t)q * N * TC_KC + ((size_t)(kl / 8) * N + (n0 + o)) * 8 + (kl % 8)] =
+                        __float2half(c->w[((size_t)o * cin + ci) * k * k + t]);
+                }
+        }
+        n0 += c->cout;
+    }
+    return img;
+}
+
+template <int MODE>
+void launch_tc(const TcArgs &a, cudaStream_t s) {
+    const long M = (long)a.nimg * a.OH * a.OW;
+    const unsigned grid = (unsigned)((M + 127) / 128);
+    const size_t smem = tc_smem_bytes(a.N);
+    switch (tc_tmem_cols(a.N)) {
+        case 32: k_tc_conv<MODE, 32><<<grid, 128, smem, s>>>(a); break;
+        case 64: k_tc_conv<MODE, 64><<<grid, 128, smem, s>>>(a); break;
+        case 128: k_tc_conv<MODE, 128><<<grid, 128, smem, s>>>(a); break;
+        default: k_tc_conv<MODE, 256><<<grid, 128, smem, s>>>(a); break;
+    }
+}
+
+template <int MODE>
+cudaError_t tc_init_mode() {
+    cudaError_t e;
+    const int smem = (int)tc_smem_bytes(256);
+    if ((e = cudaFuncSetAttribute(k_tc_conv<MODE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_tc_conv<MODE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    if ((e = cudaFuncSetAttribute(k_tc_conv<MODE, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+    return cudaFuncSetAttribute(k_tc_conv<MODE, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+cudaError_t tc_init() {
+    cudaError_t e;
+    if ((e = tc_init_mode<TC_PW>())) return e;
+    if ((e = tc_init_mode<TC_3X3>())) return e;
+    return tc_init_mode<TC_DWPW>();
+}
+
 template <typename T>
 void build_plan(rf_handle h) {
     Builder B{h, h->cfg.net_h, h->cfg.net_w};
@@ -218,6 +286,36 @@ void build_plan(rf_handle h) {
         size_t owd = B.add_weights(wd), obd = B.add_weights(dw.b);
         const int ih = cur_h, iw = cur_w, oh = cur_h / S, ow_ = cur_w / S;
         int tin = cur;
+        if constexpr (std::is_same<T, __half>::value) {
+            if (h->use_tc) {
+                // depthwise + pointwise fused on the tensor core (tc_conv.cuh TC_DWPW)
+                std::vector<float> bias;
+                int Kpad = 0;
+                std::vector<__half> img = pack_tc_weights({&pw}, bias, Kpad);
+                size_t oimg = B.add_weights_h(img), obp = B.add_weights(bias);
+                const int N = pw.cout;
+                int tpw = B.tensor("mobilenet0_relu" + std::to_string(i + 1) + "_fwd", oh, ow_, N);
+                Step s;
+                s.name = fmt("tc_dw%d+pw%d_s%d_%dto%d", i, i + 1, S, C, N);
+                s.in = {tin}; s.out = {tpw};
+                s.flops_per_img = 2.0 * oh * ow_ * C * 9 + 2.0 * oh * ow_ * C * N;
+                s.bytes_per_img = ((double)ih * iw * C + (double)oh * ow_ * N) * es;
+                s.launch = [=](int n, cudaStream_t st) {
+                    TcArgs a{};
+                    a.in = T_(tin); a.ldin = C; a.Cin = C; a.nimg = n; a.IH = ih; a.IW = iw; a.OH = oh; a.OW = ow_;
+                    a.N = N; a.K = Kpad; a.Kreal = C; a.wimg = h->d_weights_h + oimg; a.bias = Wd(obp);
+                    a.dw_w = Wd(owd); a.dw_b = Wd(obd); a.dw_stride = S;
+                    a.out = TcOut{T_(tpw), N, N, 1, nullptr, 0, 0};
+                    launch_tc<TC_DWPW>(a, st);
+                };
+                B.step(std::move(s));
+                cur = tpw; cur_h = oh; cur_w = ow_; cur_c = N;
+                if (i + 1 == 10) c1 = cur;
+                if (i + 1 == 22) c2 = cur;
+                if (i + 1 == 26) c3 = cur;
+                continue;
+            }
+        }
         int tdw = B.tensor("mobilenet0_relu" + std::to_string(i) + "_fwd", oh, ow_, C);
         {
             Step s;
@@ -260,6 +358,32 @@ void build_plan(rf_handle h) {
     // ---- FPN + SSH (prototxt:1199-2302) -----------------------------------------------------
     auto conv_step = [&](const std::string &sname, std::vector<const FoldedConv *> cs, int tin, int ih, int iw,
                          int t0, int ld0, int off0, int n0, int relu0, int t1, int ld1, int off1, int relu1) {
+        if constexpr (std::is_same<T, __half>::value) {
+            if (h->use_tc) {
+                std::vector<float> bias;
+                int Kpad = 0;
+                std::vector<__half> img = pack_tc_weights(cs, bias, Kpad);
+                size_t oimg = B.add_weights_h(img), ob = B.add_weights(bias);
+                const int N = (int)bias.size(), cin = cs[0]->cin, ks = cs[0]->k;
+                const int ldin = h->tensors[tin].c;
+                Step s;
+                s.name = "tc_" + sname;
+                s.in = {tin};
+                s.out = {t0};
+                if (t1 >= 0) s.out.push_back(t1);
+                s.flops_per_img = 2.0 * ih * iw * cin * ks * ks * N;
+                s.bytes_per_img = ((double)ih * iw * cin + (double)ih * iw * N) * es;
+                s.launch = [=](int n, cudaStream_t st) {
+                    TcArgs a{};
+                    a.in = T_(tin); a.ldin = ldin; a.Cin = cin; a.nimg = n; a.IH = ih; a.IW = iw; a.OH = ih; a.OW = iw;
+                    a.N = N; a.K = Kpad; a.Kreal = ks * ks * cin; a.wimg = h->d_weights_h + oimg; a.bias = Wd(ob);
+                    a.out = TcOut{T_(t0) + off0, ld0, n0, relu0, t1 >= 0 ? T_(t1) + off1 : nullptr, ld1, relu1};
+                    if (ks == 1) launch_tc<TC_PW>(a, st); else launch_tc<TC_3X3>(a, st);
+                };
+                B.step(std::move(s));
+                return;
+            }
+        }
         std::vector<float> bias;
         std::vector<float> wk = pack_gemm(cs, bias);
         size_t ow = B.add_weights(wk), ob = B.add_weights(bias);
@@ -452,7 +576,7 @@ void destroy(rf_handle h) {
     cudaSetDevice(h->device);
     for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->arena); cudaFree(h->d_weights); cudaFree(h->d_input); cudaFree(h->d_raw); cudaFree(h->d_params);
+    cudaFree(h->arena); cudaFree(h->d_weights); cudaFree(h->d_weights_h); cudaFree(h->d_input); cudaFree(h->d_raw); cudaFree(h->d_params);
     cudaFree(h->pb.cand_keys); cudaFree(h->pb.cand_recs); cudaFree(h->pb.cand_count); cudaFree(h->pb.sort_scratch);
     cudaFree(h->pb.flag_scratch); cudaFree(h->pb.out_dets); cudaFree(h->pb.out_counts); cudaFree(h->pb.out_total_kept);
     for (auto p : h->d_blobs) cudaFree(p);
@@ -566,11 +690,17 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
         int ap2 = 1;
         while (ap2 < A) ap2 <<= 1;
 
+        h->use_tc = h->cfg.precision == RF_PREC_FP16 && !(h->cfg.flags & RF_FLAG_NO_TENSORCORE);
+        if (h->use_tc) CK(tc_init());
         if (h->cfg.precision == RF_PREC_FP32) build_plan<float>(h); else build_plan<__half>(h);
         place_tensors(h, false);
         CK(cudaMalloc(&h->arena, h->arena_bytes));
         CK(cudaMalloc(&h->d_weights, h->wstage.size() * sizeof(float)));
         CK(cudaMemcpy(h->d_weights, h->wstage.data(), h->wstage.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (!h->wstage_h.empty()) {
+            CK(cudaMalloc(&h->d_weights_h, h->wstage_h.size() * sizeof(__half)));
+            CK(cudaMemcpy(h->d_weights_h, h->wstage_h.data(), h->wstage_h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        }
 
         const size_t in_bytes = (size_t)Bm * Hn * Wn * 3;
         CK(cudaMalloc(&h->d_input, in_bytes));
