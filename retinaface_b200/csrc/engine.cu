@@ -187,25 +187,27 @@ void launch_gemm(const T *in, int ldin, int cin, const float *wk, const float *b
 }
 
 // ---- tcgen05 path helpers --------------------------------------------------------------------
-// B operand images: per 64-wide K chunk, [k/8][n][8] halfs (the UMMA K-major no-swizzle layout of
-// tc_conv.cuh), K ordered (tap, cin); convs sharing an input are concatenated along N.
-std::vector<__half> pack_tc_weights(const std::vector<const FoldedConv *> &cs, std::vector<float> &bias, int &Kpad) {
+// B operand image [K/8][n][8] halfs (UMMA K-major no-swizzle, LBO = n*16 B), K ordered (tap, cin) and
+// zero-padded to a multiple of 16; convs sharing an input are concatenated along N; `nsplit` slices
+// of N each get their own image (slice s at s * Kpad * (N/nsplit)).
+std::vector<__half> pack_tc_weights(const std::vector<const FoldedConv *> &cs, std::vector<float> &bias, int &Kpad, int nsplit = 1) {
     const int cin = cs[0]->cin, k = cs[0]->k;
     int N = 0;
     for (auto c : cs) N += c->cout;
     const int K = k * k * cin;
     Kpad = (K + 15) / 16 * 16;
-    const int nch = (Kpad + TC_KC - 1) / TC_KC;
-    std::vector<__half> img((size_t)nch * N * TC_KC, __float2half(0.f));
+    const int Ns = N / nsplit;
+    std::vector<__half> img((size_t)Kpad * N, __float2half(0.f));
     bias.assign(N, 0.f);
     int n0 = 0;
     for (auto c : cs) {
         for (int o = 0; o < c->cout; o++) {
-            bias[n0 + o] = c->b[o];
+            const int n = n0 + o, sl = n / Ns, nl = n % Ns;
+            bias[n] = c->b[o];
             for (int ci = 0; ci < cin; ci++)
                 for (int t = 0; t < k * k; t++) {
-                    int kk = t * cin + ci, q = kk / TC_KC, kl = kk % TC_KC;
-                    img[(size_t)q * N * TC_KC + ((size_t)(kl / 8) * N + (n0 + o)) * 8 + (kl % 8)] =
+                    const int kk = t * cin + ci;
+                    img[(size_t)sl * Kpad * Ns + ((size_t)(kk / 8) * Ns + nl) * 8 + (kk % 8)] =
                         __float2half(c->w[((size_t)o * cin + ci) * k * k + t]);
                 }
         }
@@ -214,33 +216,65 @@ std::vector<__half> pack_tc_weights(const std::vector<const FoldedConv *> &cs, s
     return img;
 }
 
-template <int MODE>
-void launch_tc(const TcArgs &a, cudaStream_t s) {
-    const long M = (long)a.nimg * a.OH * a.OW;
-    const unsigned grid = (unsigned)((M + 127) / 128);
-    const size_t smem = tc_smem_bytes(a.N);
+void launch_tc_conv(const TcConvArgs &a, cudaStream_t s) {
+    const long P = (long)a.nimg * a.Hp * a.Wp;
+    const unsigned grid = (unsigned)((P + 127) / 128);
+    const size_t smem = tc_conv_smem_bytes(a);
     switch (tc_tmem_cols(a.N)) {
-        case 32: k_tc_conv<MODE, 32><<<grid, 128, smem, s>>>(a); break;
-        case 64: k_tc_conv<MODE, 64><<<grid, 128, smem, s>>>(a); break;
-        case 128: k_tc_conv<MODE, 128><<<grid, 128, smem, s>>>(a); break;
-        default: k_tc_conv<MODE, 256><<<grid, 128, smem, s>>>(a); break;
+        case 32: k_tc_conv_staged<32><<<grid, TC_THREADS, smem, s>>>(a); break;
+        case 64: k_tc_conv_staged<64><<<grid, TC_THREADS, smem, s>>>(a); break;
+        case 128: k_tc_conv_staged<128><<<grid, TC_THREADS, smem, s>>>(a); break;
+        default: k_tc_conv_staged<256><<<grid, TC_THREADS, smem, s>>>(a); break;
     }
 }
-
-template <int MODE>
-cudaError_t tc_init_mode() {
-    cudaError_t e;
-    const int smem = (int)tc_smem_bytes(256);
-    if ((e = cudaFuncSetAttribute(k_tc_conv<MODE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_tc_conv<MODE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_tc_conv<MODE, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-    return cudaFuncSetAttribute(k_tc_conv<MODE, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+void launch_tc_dwpw(const TcDwArgs &a, int nsplit, cudaStream_t s) {
+    const long M = (long)a.nimg * a.OH * a.OW;
+    dim3 grid((unsigned)((M + a.rows - 1) / a.rows), nsplit);
+    const size_t smem = tc_dw_smem_bytes(a);
+    switch (tc_tmem_cols(a.N)) {
+        case 32: k_tc_dwpw_staged<32><<<grid, TC_THREADS, smem, s>>>(a); break;
+        case 64: k_tc_dwpw_staged<64><<<grid, TC_THREADS, smem, s>>>(a); break;
+        case 128: k_tc_dwpw_staged<128><<<grid, TC_THREADS, smem, s>>>(a); break;
+        default: k_tc_dwpw_staged<256><<<grid, TC_THREADS, smem, s>>>(a); break;
+    }
 }
+constexpr int TC_SMEM_LIMIT = 200 * 1024;   // dynamic; the kernels also hold ~20 KB static
 cudaError_t tc_init() {
     cudaError_t e;
-    if ((e = tc_init_mode<TC_PW>())) return e;
-    if ((e = tc_init_mode<TC_3X3>())) return e;
-    return tc_init_mode<TC_DWPW>();
+#define RF_TC_ATTR(K_) if ((e = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT))) return e
+    RF_TC_ATTR(k_tc_conv_staged<32>); RF_TC_ATTR(k_tc_conv_staged<64>); RF_TC_ATTR(k_tc_conv_staged<128>); RF_TC_ATTR(k_tc_conv_staged<256>);
+    RF_TC_ATTR(k_tc_dwpw_staged<32>); RF_TC_ATTR(k_tc_dwpw_staged<64>); RF_TC_ATTR(k_tc_dwpw_staged<128>); RF_TC_ATTR(k_tc_dwpw_staged<256>);
+#undef RF_TC_ATTR
+    return cudaSuccess;
+}
+
+// Tile geometry of one fused depthwise+pointwise layer: rows per CTA, N slices and the exact upper
+// bound of the staged range, so that everything fits in shared memory.
+struct DwGeom { int rows, nsplit, Rmax; };
+DwGeom dw_geometry(int C, int N, int IH, int IW, int S) {
+    const int OH = IH / S, OW = IW / S, Wp = IW + 2, Hp = IH + 1, Kpad = (C + 15) / 16 * 16;
+    auto centre = [&](long m) { long ox = m % OW, oy = (m / OW) % OH, b = m / ((long)OW * OH); return (b * Hp + oy * S) * Wp + ox * S + 1; };
+    for (int rows : {128, 64}) {
+        if (rows == 128 && OH * OW <= 28 * 28) continue;   // small maps: more, smaller CTAs (latency bound)
+        for (int nsplit : {1, 2, 4}) {
+            if ((N / nsplit) % 16) continue;
+            // tile starts shift against image boundaries with period lcm(rows, OH*OW): scan one full period
+            // (+1 image) so that every alignment, including tiles straddling two images, is covered
+            long g = rows, t = (long)OH * OW;
+            while (t) { long u = g % t; g = t; t = u; }
+            const long M = ((long)rows / g + 1) * OH * OW;
+            int R = 0;
+            for (long m0 = 0; m0 < M; m0 += rows) {
+                long ml = std::min(m0 + rows, M) - 1;
+                R = std::max(R, (int)(centre(ml) - centre(m0) + 2 * (Wp + 1) + 1));
+            }
+            R |= 1;
+            TcDwArgs a{};
+            a.C = C; a.Rmax = R; a.Kpad = Kpad; a.N = N / nsplit;
+            if (R <= TC_MAX_R && tc_dw_smem_bytes(a) <= (size_t)TC_SMEM_LIMIT) return {rows, nsplit, R};
+        }
+    }
+    return {0, 0, 0};
 }
 
 template <typename T>
@@ -288,12 +322,14 @@ void build_plan(rf_handle h) {
         int tin = cur;
         if constexpr (std::is_same<T, __half>::value) {
             if (h->use_tc) {
-                // depthwise + pointwise fused on the tensor core (tc_conv.cuh TC_DWPW)
+                // depthwise + pointwise fused: stencil from staged shared memory -> tcgen05 GEMM (tc_conv.cuh)
+                const int N = pw.cout;
+                const DwGeom geo = dw_geometry(C, N, ih, iw, S);
+                if (geo.rows == 0) throw CudaFail{cudaErrorInvalidConfiguration, "dw_geometry: layer does not fit shared memory", __FILE__, __LINE__};
                 std::vector<float> bias;
                 int Kpad = 0;
-                std::vector<__half> img = pack_tc_weights({&pw}, bias, Kpad);
+                std::vector<__half> img = pack_tc_weights({&pw}, bias, Kpad, geo.nsplit);
                 size_t oimg = B.add_weights_h(img), obp = B.add_weights(bias);
-                const int N = pw.cout;
                 int tpw = B.tensor("mobilenet0_relu" + std::to_string(i + 1) + "_fwd", oh, ow_, N);
                 Step s;
                 s.name = fmt("tc_dw%d+pw%d_s%d_%dto%d", i, i + 1, S, C, N);
@@ -301,12 +337,11 @@ void build_plan(rf_handle h) {
                 s.flops_per_img = 2.0 * oh * ow_ * C * 9 + 2.0 * oh * ow_ * C * N;
                 s.bytes_per_img = ((double)ih * iw * C + (double)oh * ow_ * N) * es;
                 s.launch = [=](int n, cudaStream_t st) {
-                    TcArgs a{};
-                    a.in = T_(tin); a.ldin = C; a.Cin = C; a.nimg = n; a.IH = ih; a.IW = iw; a.OH = oh; a.OW = ow_;
-                    a.N = N; a.K = Kpad; a.Kreal = C; a.wimg = h->d_weights_h + oimg; a.bias = Wd(obp);
-                    a.dw_w = Wd(owd); a.dw_b = Wd(obd); a.dw_stride = S;
-                    a.out = TcOut{T_(tpw), N, N, 1, nullptr, 0, 0};
-                    launch_tc<TC_DWPW>(a, st);
+                    TcDwArgs a{};
+                    a.in = T_(tin); a.C = C; a.nimg = n; a.IH = ih; a.IW = iw; a.OH = oh; a.OW = ow_; a.S = S;
+                    a.N = N / geo.nsplit; a.Ntotal = N; a.Kpad = Kpad; a.rows = geo.rows; a.Wp = iw + 2; a.Hp = ih + 1; a.Rmax = geo.Rmax;
+                    a.wimg = h->d_weights_h + oimg; a.bias = Wd(obp); a.dw_w = Wd(owd); a.dw_b = Wd(obd); a.out = T_(tpw);
+                    launch_tc_dwpw(a, geo.nsplit, st);
                 };
                 B.step(std::move(s));
                 cur = tpw; cur_h = oh; cur_w = ow_; cur_c = N;
@@ -365,7 +400,6 @@ void build_plan(rf_handle h) {
                 std::vector<__half> img = pack_tc_weights(cs, bias, Kpad);
                 size_t oimg = B.add_weights_h(img), ob = B.add_weights(bias);
                 const int N = (int)bias.size(), cin = cs[0]->cin, ks = cs[0]->k;
-                const int ldin = h->tensors[tin].c;
                 Step s;
                 s.name = "tc_" + sname;
                 s.in = {tin};
@@ -374,11 +408,13 @@ void build_plan(rf_handle h) {
                 s.flops_per_img = 2.0 * ih * iw * cin * ks * ks * N;
                 s.bytes_per_img = ((double)ih * iw * cin + (double)ih * iw * N) * es;
                 s.launch = [=](int n, cudaStream_t st) {
-                    TcArgs a{};
-                    a.in = T_(tin); a.ldin = ldin; a.Cin = cin; a.nimg = n; a.IH = ih; a.IW = iw; a.OH = ih; a.OW = iw;
-                    a.N = N; a.K = Kpad; a.Kreal = ks * ks * cin; a.wimg = h->d_weights_h + oimg; a.bias = Wd(ob);
+                    TcConvArgs a{};
+                    a.in = T_(tin); a.Cin = cin; a.nimg = n; a.H = ih; a.W = iw; a.taps = ks * ks; a.N = N;
+                    a.Wp = ks == 3 ? iw + 2 : iw; a.Hp = ks == 3 ? ih + 1 : ih;
+                    a.R = (ks == 3 ? 128 + 2 * (iw + 3) : 128) | 1;
+                    a.wimg = h->d_weights_h + oimg; a.bias = Wd(ob);
                     a.out = TcOut{T_(t0) + off0, ld0, n0, relu0, t1 >= 0 ? T_(t1) + off1 : nullptr, ld1, relu1};
-                    if (ks == 1) launch_tc<TC_PW>(a, st); else launch_tc<TC_3X3>(a, st);
+                    launch_tc_conv(a, st);
                 };
                 B.step(std::move(s));
                 return;

@@ -27,15 +27,21 @@ namespace {
 struct Tap { int s0, s1, a0, a1; };
 
 // OpenCV resizeGeneric_ linear coefficient of one destination coordinate (resize.cpp, INTER_LINEAR).
+// Horizontal taps zero the fraction at the borders (xmin/xmax handling); vertical taps keep the
+// fraction and clamp the source ROW indices instead (resizeGeneric_Invoker: sy = clip(sy0 + k, 0, h)),
+// which differs by one count after the truncating vertical pass.
+template <bool HORIZONTAL>
 __device__ __forceinline__ Tap tap_of(int d, int sn, double scale) {
     float fx = (float)((d + 0.5) * scale - 0.5);
     int s = (int)floorf(fx);
     fx -= (float)s;
-    if (s < 0) { fx = 0.f; s = 0; }
-    if (s >= sn - 1) { fx = 0.f; s = sn - 1; }
+    if (HORIZONTAL) {
+        if (s < 0) { fx = 0.f; s = 0; }
+        if (s >= sn - 1) { fx = 0.f; s = sn - 1; }
+    }
     Tap t;
-    t.s0 = s;
-    t.s1 = min(s + 1, sn - 1);
+    t.s0 = min(max(s, 0), sn - 1);
+    t.s1 = min(max(s + 1, 0), sn - 1);
     t.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f));   // saturate_cast<short>(cbuf*INTER_RESIZE_COEF_SCALE)
     t.a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
     return t;
@@ -54,7 +60,7 @@ __global__ void __launch_bounds__(256) k_letterbox(const uint8_t *__restrict__ s
         o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
         return;
     }
-    const Tap tx = tap_of(x, sw, scale), ty = tap_of(y, sh, scale);
+    const Tap tx = tap_of<true>(x, sw, scale), ty = tap_of<false>(y, sh, scale);
     const uint8_t *r0 = src + (size_t)ty.s0 * sw * 3, *r1 = src + (size_t)ty.s1 * sw * 3;
 #pragma unroll
     for (int c = 0; c < 3; c++) {

@@ -27,31 +27,11 @@
 
 namespace rf {
 
-enum TcMode { TC_PW = 0, TC_3X3 = 1, TC_DWPW = 2 };
-
-constexpr int TC_KC = 64;                      // K elements per pipeline chunk
 constexpr int TC_LBO_A = 128 * 16 + 16;        // bytes between 8-channel groups of the A tile
-constexpr int TC_A_STAGE = (TC_KC / 8) * TC_LBO_A;   // 16,512 B
 
 struct TcOut {
     __half *p0; int ld0; int n0; int relu0;    // channels [0, n0)  -> p0[m*ld0 + n]
     __half *p1; int ld1; int relu1;            // channels [n0, N)  -> p1[m*ld1 + n - n0]
-};
-
-struct TcArgs {
-    const __half *in;       // NHWC input, pixel stride = ldin
-    int ldin, Cin;
-    int nimg, IH, IW;       // input spatial size
-    int OH, OW;             // output spatial size (== input except stride-2 depthwise)
-    int N;                  // output channels
-    int K;                  // taps * Cin (TC_DWPW: Cin), rounded up to a multiple of 16
-    int Kreal;              // un-padded K: A groups at or beyond it are zero (Cin = 8 layer)
-    const __half *wimg;     // packed B chunk images, chunk q at q * (N * TC_KC) halfs
-    const float *bias;      // [N]
-    const float *dw_w;      // TC_DWPW: [9][Cin] folded depthwise weights
-    const float *dw_b;      // TC_DWPW: [Cin]
-    int dw_stride;
-    TcOut out;
 };
 
 namespace tc {
@@ -131,151 +111,63 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 constexpr int tc_tmem_cols(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)); }
 
-// dynamic shared memory: 2 stages x (A tile + B chunk image)
-inline size_t tc_smem_bytes(int N) { return 2 * ((size_t)TC_A_STAGE + (size_t)N * TC_KC * 2) + 128; }
+// =============================================================================================
+// v2 kernels: "staged range + shifted descriptors".
+//
+// The input pixels a 128-row tile needs form ONE contiguous range of a zero-padded linear
+// position space: position p <-> (image b, row yy in [0,H], column xx in [0,W+1]) with
+// p = (b*(H+1) + yy)*(W+2) + xx; xx = 0 / W+1 and yy = H are zero padding (one shared zero row
+// between consecutive images).  The range is staged ONCE into shared memory as
+// [channel group g][position][8 halfs] (16 B per item, cp.async with zero-fill for padding), which
+// is exactly the UMMA canonical K-major no-swizzle layout with SBO = 128 B and LBO = R*16 B.  In
+// this space a 3x3 tap is a constant position shift dy*(W+2)+dx, so the A operand of every tap is
+// the SAME staged buffer with the descriptor start address moved by shift*16 bytes: the im2col
+// matrix is never materialised, not even in shared memory.  GEMM rows enumerate padded positions
+// (W/(W+2) of them are real pixels; results of padding rows are discarded).
+// =============================================================================================
+constexpr int TC_THREADS = 256;
+constexpr int TC_MAX_R = 2048;     // staged positions per tile (table size)
 
-template <int MODE, int NT /* TMEM columns: 32/64/128/256 */>
-__global__ void __launch_bounds__(128) k_tc_conv(const TcArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_full[2];    // B chunk landed (complete_tx)
-    __shared__ __align__(8) uint64_t bar_free[2];    // MMAs that read this stage have retired
-    __shared__ __align__(8) uint64_t bar_done;       // all MMAs of the tile retired
-    __shared__ uint32_t s_tmem;
-    __shared__ int s_pb[128], s_py[128], s_px[128];  // output pixel -> (image, oy, ox); pb < 0: row beyond M
-    __shared__ float s_dw[MODE == TC_DWPW ? 10 * 256 : 1];
+struct TcConvArgs {
+    const __half *in;       // NHWC dense [nimg][H][W][Cin]
+    int Cin, nimg, H, W;
+    int taps;               // 1 (pointwise) or 9 (3x3, pad 1)
+    int N;                  // output channels (multiple of 16, <= 256)
+    int Wp, Hp;             // padded geometry: taps==9 ? (W+2, H+1) : (W, H)
+    int R;                  // staged positions per tile (odd): 128 + 2*(Wp+1) for 3x3, 129 for 1x1
+    const __half *wimg;     // B image [K/8][N][8] halfs, K = taps*Cin ordered (tap, cin)
+    const float *bias;      // [N]
+    TcOut out;
+};
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int N = a.N;
-    const size_t b_stage_bytes = (size_t)N * TC_KC * 2;
-    unsigned char *sA[2] = {smem, smem + TC_A_STAGE};
-    unsigned char *sB[2] = {smem + 2 * TC_A_STAGE, smem + 2 * TC_A_STAGE + b_stage_bytes};
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, bool valid) {
+    const unsigned sz = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
-    const long M = (long)a.nimg * a.OH * a.OW;
-    const long m0 = (long)blockIdx.x * 128;
-    {
-        long m = m0 + tid;
-        if (m < M) {
-            s_px[tid] = (int)(m % a.OW);
-            s_py[tid] = (int)((m / a.OW) % a.OH);
-            s_pb[tid] = (int)(m / ((long)a.OW * a.OH));
-        } else {
-            s_pb[tid] = -1; s_py[tid] = 0; s_px[tid] = 0;
-        }
-    }
-    if (MODE == TC_DWPW) {
-        for (int i = tid; i < 9 * a.Cin; i += 128) s_dw[i] = a.dw_w[i];
-        for (int i = tid; i < a.Cin; i += 128) s_dw[9 * 256 + i] = a.dw_b[i];
-    }
-    if (tid == 0) {
-        tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
-        tc::mbar_init(&bar_free[0], 1); tc::mbar_init(&bar_free[1], 1);
-        tc::mbar_init(&bar_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) tc::tmem_alloc<NT>(&s_tmem);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem = s_tmem;
-
-    const int K = a.K;
-    const int nchunks = (K + TC_KC - 1) / TC_KC;
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-    for (int q = 0; q < nchunks; q++) {
-        const int st = q & 1;
-        const int use = q >> 1;                          // how many times this stage was used before
-        const int kc = min(TC_KC, K - q * TC_KC);        // K elements in this chunk (multiple of 16)
-        if (use > 0) tc::mbar_wait(&bar_free[st], (use - 1) & 1);
-        // ---- B chunk: one TMA bulk copy of the pre-packed image --------------------------------
-        if (tid == 0) {
-            const unsigned bytes = (unsigned)((size_t)N * kc * 2);
-            tc::mbar_expect_tx(&bar_full[st], bytes);
-            tc::bulk_g2s(sB[st], a.wimg + (size_t)q * N * TC_KC, bytes, &bar_full[st]);
-        }
-        // ---- A chunk: 128 rows x kc channels, 16-byte items (row, 8-channel group) ---------------
-        const int G = kc >> 3;                           // groups in this chunk (2, 4, 8 ...)
-        for (int it = tid; it < 128 * G; it += 128) {
-            const int g = it % G, r = it / G;
-            const int kidx = q * TC_KC + g * 8;          // global K index of this group
-            uint4 v = make_uint4(0, 0, 0, 0);
-            const int pb = s_pb[r];
-            if (pb >= 0 && kidx < a.Kreal) {
-                if (MODE == TC_DWPW) {
-                    // depthwise 3x3 (+BN+ReLU) of channels [kidx, kidx+8) at output pixel r
-                    const int c0 = kidx;
-                    float acc[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) acc[i] = s_dw[9 * 256 + c0 + i];
-                    const int S = a.dw_stride;
-                    const __half *base = a.in + (size_t)pb * a.IH * a.IW * a.ldin + c0;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ky++) {
-                        const int iy = s_py[r] * S + ky - 1;
-                        if (iy < 0 || iy >= a.IH) continue;
-#pragma unroll
-                        for (int kx = 0; kx < 3; kx++) {
-                            const int ix = s_px[r] * S + kx - 1;
-                            if (ix < 0 || ix >= a.IW) continue;
-                            Vec8<__half> x;
-                            x.load(base + ((size_t)iy * a.IW + ix) * a.ldin);
-                            float f[8];
-                            x.to_float(f);
-                            const float *wr = &s_dw[(ky * 3 + kx) * a.Cin + c0];
-#pragma unroll
-                            for (int i = 0; i < 8; i++) acc[i] = fmaf(f[i], wr[i], acc[i]);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; i++) acc[i] = fmaxf(acc[i], 0.f);
-                    Vec8<__half> o;
-                    o.from_float(acc);
-                    v = o.v;
-                } else {
-                    const int tap = MODE == TC_3X3 ? kidx / a.Cin : 0;
-                    const int c0 = MODE == TC_3X3 ? kidx - tap * a.Cin : kidx;
-                    const int iy = s_py[r] + (MODE == TC_3X3 ? tap / 3 - 1 : 0);
-                    const int ix = s_px[r] + (MODE == TC_3X3 ? tap % 3 - 1 : 0);
-                    if (iy >= 0 && iy < a.IH && ix >= 0 && ix < a.IW)
-                        v = *reinterpret_cast<const uint4 *>(a.in + (((size_t)pb * a.IH + iy) * a.IW + ix) * a.ldin + c0);
-                }
-            }
-            *reinterpret_cast<uint4 *>(sA[st] + g * TC_LBO_A + r * 16) = v;
-        }
-        tc::fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        // ---- MMA: one thread issues kc/16 instructions -------------------------------------------
-        if (tid == 0) {
-            tc::mbar_wait(&bar_full[st], use & 1);       // weights landed
-            tc::tc_fence_after();
-            const uint32_t a_addr = tc::smem_u32(sA[st]), b_addr = tc::smem_u32(sB[st]);
-            const uint32_t lbo_b = (uint32_t)N * 16;
-            for (int ks = 0; ks < kc / 16; ks++) {
-                const uint64_t ad = tc::smem_desc(a_addr + ks * 2 * TC_LBO_A, TC_LBO_A, 128);
-                const uint64_t bd = tc::smem_desc(b_addr + ks * 2 * lbo_b, lbo_b, 128);
-                tc::mma_f16(tmem, ad, bd, idesc, (q > 0 || ks > 0) ? 1u : 0u);
-            }
-            tc::mma_commit(&bar_free[st]);               // frees this stage when the MMAs retire
-            if (q == nchunks - 1) tc::mma_commit(&bar_done);
-        }
-    }
-    // ---- epilogue: TMEM -> registers -> bias/ReLU -> FP16 -> global ---------------------------------
-    tc::mbar_wait(&bar_done, 0);
-    tc::tc_fence_after();
-    const long m = m0 + tid;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int n0 = 0; n0 < N; n0 += 16) {
+// Epilogue shared by both kernels: 8 warps; warp w reads TMEM lane quadrant (w & 3) and the 16-column
+// blocks j with (j & 1) == (w >> 2); thread = one GEMM row.
+__device__ __forceinline__ void tc_epilogue(uint32_t tmem, int N, const float *__restrict__ bias, const TcOut &o, long out_row,
+                                            int n_off) {
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int j = warp >> 2; j < (N >> 4); j += 2) {
+        const int n0 = j * 16;
         uint32_t r[16];
         tc::tmem_ld16(lane_addr + n0, r);
         tc::tmem_ld_wait();
-        if (m < M) {
-            const bool first = n0 < a.out.n0;
-            const int relu = first ? a.out.relu0 : a.out.relu1;
-            __half *dst = first ? a.out.p0 + (size_t)m * a.out.ld0 + n0 : a.out.p1 + (size_t)m * a.out.ld1 + (n0 - a.out.n0);
+        if (out_row >= 0) {
+            const int gn = n_off + n0;          // channel index in the layer's full output
+            const bool first = gn < o.n0;
+            const int relu = first ? o.relu0 : o.relu1;
+            __half *dst = first ? o.p0 + (size_t)out_row * o.ld0 + gn : o.p1 + (size_t)out_row * o.ld1 + (gn - o.n0);
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                f[i] = __uint_as_float(r[i]) + __ldg(a.bias + n0 + i);
+                f[i] = __uint_as_float(r[i]) + __ldg(bias + gn + i);
                 if (relu) f[i] = fmaxf(f[i], 0.f);
             }
             Vec8<__half> o0, o1;
@@ -285,9 +177,243 @@ __global__ void __launch_bounds__(128) k_tc_conv(const TcArgs a) {
             o1.store(dst + 8);
         }
     }
+}
+
+inline size_t tc_conv_smem_bytes(const TcConvArgs &a) {
+    return (size_t)(a.Cin / 8) * a.R * 16 + (size_t)a.taps * a.Cin * a.N * 2 + 128;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar_b, bar_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_off[TC_MAX_R];      // staged position -> element offset of its pixel in `in`, -1 = zero padding
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int pad = a.taps == 9 ? 1 : 0;
+    const int G = a.Cin >> 3;
+    const uint32_t lbo_s = (uint32_t)a.R * 16;
+    unsigned char *sS = smem;
+    unsigned char *sB = smem + (size_t)G * lbo_s;
+    const long P = (long)a.nimg * a.Hp * a.Wp;
+    const long m0 = (long)blockIdx.x * 128;
+    const long lo = m0 - (long)(a.Wp + 1) * pad;
+
+    if (tid == 0) {
+        tc::mbar_init(&bar_b, 1);
+        tc::mbar_init(&bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)((size_t)a.taps * a.Cin * a.N * 2);
+        tc::mbar_expect_tx(&bar_b, bytes);
+        tc::bulk_g2s(sB, a.wimg, bytes, &bar_b);     // all taps' weights: one TMA bulk copy
+    }
+    if (warp == 1) tc::tmem_alloc<NT>(&s_tmem);
+    for (int pl = tid; pl < a.R; pl += TC_THREADS) {
+        const long p = lo + pl;
+        int off = -1;
+        if (p >= 0 && p < P) {
+            const int b = (int)(p / (a.Hp * a.Wp));
+            const int rem = (int)(p - (long)b * a.Hp * a.Wp);
+            const int yy = rem / a.Wp, xx = rem - yy * a.Wp;
+            if (yy < a.H && xx >= pad && xx < a.W + pad) off = ((b * a.H + yy) * a.W + (xx - pad)) * a.Cin;
+        }
+        s_off[pl] = off;
+    }
+    __syncthreads();
+    // ---- stage the range: item = (position, 8-channel group), 16 B each --------------------------------
+    for (int it = tid; it < a.R * G; it += TC_THREADS) {
+        const int g = it % G, pl = it / G;
+        const int off = s_off[pl];
+        cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (off >= 0 ? off + g * 8 : 0), off >= 0);
+    }
+    cp_async_wait_all();
+    tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<NT>(tmem);
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    // ---- MMA: taps * Cin/16 instructions, A = shifted views of the one staged buffer --------------------
+    if (tid == 0) {
+        tc::mbar_wait(&bar_b, 0);
+        tc::tc_fence_after();
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(a.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t s_addr = tc::smem_u32(sS), b_addr = tc::smem_u32(sB);
+        const uint32_t lbo_b = (uint32_t)a.N * 16;
+        const int row_base = (int)(m0 - lo);
+        uint32_t acc = 0;
+        for (int t = 0; t < a.taps; t++) {
+            const int shift = pad ? (t / 3 - 1) * a.Wp + (t % 3 - 1) : 0;
+            for (int cs = 0; cs < (a.Cin >> 4); cs++) {
+                const uint64_t ad = tc::smem_desc(s_addr + (uint32_t)(2 * cs) * lbo_s + (uint32_t)(row_base + shift) * 16, lbo_s, 128);
+                const uint64_t bd = tc::smem_desc(b_addr + (uint32_t)(t * G + 2 * cs) * lbo_b, lbo_b, 128);
+                tc::mma_f16(tmem, ad, bd, idesc, acc);
+                acc = 1;
+            }
+        }
+        tc::mma_commit(&bar_done);
+    }
+    // ---- epilogue ---------------------------------------------------------------------------------------
+    tc::mbar_wait(&bar_done, 0);
+    tc::tc_fence_after();
+    {
+        const int r = (warp & 3) * 32 + (tid & 31);
+        const int off = s_off[(int)(m0 - lo) + r];               // element offset / Cin == output pixel index
+        tc_epilogue(tmem, a.N, a.bias, a.out, off >= 0 ? (long)(off / a.Cin) : -1, 0);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<NT>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused depthwise 3x3 (stride 1|2) + BN + ReLU -> pointwise 1x1 + BN + ReLU.
+// The input range of the tile is staged as above; the depthwise stencil is evaluated from shared
+// memory on CUDA cores (FP32 accumulate, FP16 round -- the same rounding point as the unfused
+// layer pair) straight into the tensor-core A operand; the pointwise GEMM runs on tcgen05.
+// rows: 64 or 128 output pixels per CTA (the UMMA tile is always M=128; spare rows are ignored);
+// blockIdx.y selects a slice of N output channels (keeps the weight image within shared memory).
+// ---------------------------------------------------------------------------------------------
+struct TcDwArgs {
+    const __half *in;       // NHWC dense [nimg][IH][IW][C]
+    int C, nimg, IH, IW, OH, OW, S;
+    int N;                  // output channels of this CTA slice
+    int Ntotal;             // layer output channels (pixel stride of out)
+    int Kpad;               // C rounded up to 16
+    int rows;               // output pixels per CTA (64 | 128)
+    int Wp, Hp;             // IW + 2, IH + 1
+    int Rmax;               // staged positions, upper bound over tiles (odd)
+    const __half *wimg;     // slice s at s * Kpad * N halfs: [Kpad/8][N][8]
+    const float *bias;      // [Ntotal]
+    const float *dw_w, *dw_b;   // [9][C], [C]
+    __half *out;            // [nimg][OH][OW][Ntotal]
+};
+
+inline size_t tc_dw_smem_bytes(const TcDwArgs &a) {
+    return (size_t)((a.C + 7) / 8) * a.Rmax * 16 + (size_t)(a.Kpad / 8) * TC_LBO_A + (size_t)a.Kpad * a.N * 2 + 128;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar_b, bar_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_off[TC_MAX_R];
+    __shared__ int s_cpos[128];          // GEMM row -> staged index of its stencil centre, -1 = no output
+    __shared__ float s_dw[10 * 256];
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int G = a.C >> 3;
+    const uint32_t lbo_s = (uint32_t)a.Rmax * 16;
+    unsigned char *sS = smem;
+    unsigned char *sA = smem + (size_t)G * lbo_s;
+    unsigned char *sB = sA + (size_t)(a.Kpad / 8) * TC_LBO_A;
+    const long M = (long)a.nimg * a.OH * a.OW;
+    const long m0 = (long)blockIdx.x * a.rows;
+    const long mlast = min(m0 + a.rows, M) - 1;
+    auto centre = [&](long m) -> long {
+        const int ox = (int)(m % a.OW), oy = (int)((m / a.OW) % a.OH), b = (int)(m / ((long)a.OW * a.OH));
+        return ((long)b * a.Hp + (long)oy * a.S) * a.Wp + (long)ox * a.S + 1;
+    };
+    const long lo = centre(m0) - a.Wp - 1;
+    const int R = (int)(centre(mlast) + a.Wp + 1 - lo) + 1;
+    if (R > a.Rmax) __trap();            // host-side geometry (engine.cu dw_geometry) must bound every tile
+    const long P = (long)a.nimg * a.Hp * a.Wp;
+
+    if (tid == 0) {
+        tc::mbar_init(&bar_b, 1);
+        tc::mbar_init(&bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)((size_t)a.Kpad * a.N * 2);
+        tc::mbar_expect_tx(&bar_b, bytes);
+        tc::bulk_g2s(sB, a.wimg + (size_t)blockIdx.y * a.Kpad * a.N, bytes, &bar_b);
+    }
+    if (warp == 1) tc::tmem_alloc<NT>(&s_tmem);
+    for (int i = tid; i < 9 * a.C; i += TC_THREADS) s_dw[i] = a.dw_w[i];
+    for (int i = tid; i < a.C; i += TC_THREADS) s_dw[9 * 256 + i] = a.dw_b[i];
+    for (int pl = tid; pl < R; pl += TC_THREADS) {
+        const long p = lo + pl;
+        int off = -1;
+        if (p >= 0 && p < P) {
+            const int b = (int)(p / (a.Hp * a.Wp));
+            const int rem = (int)(p - (long)b * a.Hp * a.Wp);
+            const int yy = rem / a.Wp, xx = rem - yy * a.Wp;
+            if (yy < a.IH && xx >= 1 && xx <= a.IW) off = ((b * a.IH + yy) * a.IW + (xx - 1)) * a.C;
+        }
+        s_off[pl] = off;
+    }
+    if (tid < 128) {
+        const long m = m0 + tid;
+        s_cpos[tid] = (tid < a.rows && m < M) ? (int)(centre(m) - lo) : -1;
+    }
+    __syncthreads();
+    for (int it = tid; it < R * G; it += TC_THREADS) {
+        const int g = it % G, pl = it / G;
+        const int off = s_off[pl];
+        cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (off >= 0 ? off + g * 8 : 0), off >= 0);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- depthwise stencil from shared memory -> A operand (canonical K-major layout) -------------------
+    const int GA = a.Kpad >> 3;          // A groups (== G except the Cin = 8 layer: 2, second one zero)
+    for (int it = tid; it < 128 * GA; it += TC_THREADS) {
+        const int g = it % GA, r = it / GA;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        const int cp = s_cpos[r];
+        if (cp >= 0 && g < G) {
+            const int c0 = g * 8;
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = s_dw[9 * 256 + c0 + i];
+            const unsigned char *base = sS + (size_t)g * lbo_s + (size_t)cp * 16;
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                const int shift = (t / 3 - 1) * a.Wp + (t % 3 - 1);
+                Vec8<__half> x;
+                x.v = *reinterpret_cast<const uint4 *>(base + shift * 16);
+                float f[8];
+                x.to_float(f);
+                const float *wr = &s_dw[t * a.C + c0];
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] = fmaf(f[i], wr[i], acc[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = fmaxf(acc[i], 0.f);
+            Vec8<__half> o;
+            o.from_float(acc);
+            v = o.v;
+        }
+        *reinterpret_cast<uint4 *>(sA + (size_t)g * TC_LBO_A + (size_t)r * 16) = v;
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (tid == 0) {
+        tc::mbar_wait(&bar_b, 0);
+        tc::tc_fence_after();
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(a.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_addr = tc::smem_u32(sA), b_addr = tc::smem_u32(sB);
+        const uint32_t lbo_b = (uint32_t)a.N * 16;
+        for (int ks = 0; ks < (a.Kpad >> 4); ks++) {
+            const uint64_t ad = tc::smem_desc(a_addr + (uint32_t)(2 * ks) * TC_LBO_A, TC_LBO_A, 128);
+            const uint64_t bd = tc::smem_desc(b_addr + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
+            tc::mma_f16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        }
+        tc::mma_commit(&bar_done);
+    }
+    tc::mbar_wait(&bar_done, 0);
+    tc::tc_fence_after();
+    {
+        const int r = (warp & 3) * 32 + (tid & 31);
+        const long m = m0 + r;
+        TcOut o{a.out, a.Ntotal, a.Ntotal, 1, nullptr, 0, 0};
+        tc_epilogue(tmem, a.N, a.bias, o, (r < a.rows && m < M) ? m : -1, (int)blockIdx.y * a.N);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<NT>(tmem);
 }
 
 }  // namespace rf
