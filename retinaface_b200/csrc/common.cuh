@@ -39,6 +39,26 @@ template <typename T> __device__ __forceinline__ T from_f(float x);
 template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
 template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Every kernel of the forward pass is launched with cudaLaunchAttributeProgrammaticStreamSerialization:
+// its CTAs may start while the previous kernel drains.  pdl_trigger() lets the NEXT kernel start its
+// own prologue (barrier init, TMEM allocation, weight copies -- nothing that depends on activations);
+// pdl_wait() blocks until the PREVIOUS kernel has completed and its global writes are visible, and
+// must precede the first read of an activation and the first global write.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- post-process shared structures -------------------------------------------------------
 struct LevelDesc {           // one FPN level of one launch
     int stride, h, w;        // feature map size

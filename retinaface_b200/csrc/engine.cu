@@ -60,6 +60,9 @@ struct Step {
     std::vector<int> in, out;
     std::function<void(int /*n*/, cudaStream_t)> launch;
     double flops_per_img = 0, bytes_per_img = 0;  // algorithmic
+    int lane = 0;                 // 0 = main stream; 1, 2 = side branches of the forward graph
+    std::vector<int> deps;        // producer steps in OTHER lanes this step must wait for (filled by link_steps)
+    bool signals = false;         // some step in another lane waits for this one
 };
 
 }  // namespace
@@ -105,6 +108,8 @@ struct rf_handle_s {
     rf_det *h_dets = nullptr;         // pinned [max_batch][max_faces]
     int *h_counts = nullptr;          // pinned [2*max_batch]: kept, candidates
     std::map<int, cudaGraphExec_t> graphs;
+    cudaStream_t lane_stream[3] = {nullptr, nullptr, nullptr};   // [0] unused (the caller's stream is lane 0)
+    std::vector<cudaEvent_t> step_event;
     bool blobs_in_plan = false;       // head step writes blobs (forward_heads path)
     static constexpr int kParamSlots = 1024;
     unsigned param_seq = 0;
@@ -180,7 +185,7 @@ void launch_gemm(const T *in, int ldin, int cin, const float *wk, const float *b
     long M = (long)n * H * W;
     int bn = (N % 64 == 0) ? 64 : (N % 32 == 0 ? 32 : 16);
     dim3 grid((unsigned)((M + 63) / 64), (N + bn - 1) / bn);
-#define RF_GEMM(BN_, KS_) k_conv_gemm<T, BN_, KS_><<<grid, 256, 0, s>>>(in, ldin, cin, wk, bias, N, outs, n, H, W)
+#define RF_GEMM(BN_, KS_) launch_k(k_conv_gemm<T, BN_, KS_>, grid, dim3(256), 0, s, in, ldin, cin, wk, bias, N, outs, n, H, W)
     if (ks == 1) { if (bn == 64) RF_GEMM(64, 1); else if (bn == 32) RF_GEMM(32, 1); else RF_GEMM(16, 1); }
     else { if (bn == 64) RF_GEMM(64, 3); else if (bn == 32) RF_GEMM(32, 3); else RF_GEMM(16, 3); }
 #undef RF_GEMM
@@ -221,10 +226,10 @@ void launch_tc_conv(const TcConvArgs &a, cudaStream_t s) {
     const unsigned grid = (unsigned)((P + 127) / 128);
     const size_t smem = tc_conv_smem_bytes(a);
     switch (tc_tmem_cols(a.N)) {
-        case 32: k_tc_conv_staged<32><<<grid, TC_THREADS, smem, s>>>(a); break;
-        case 64: k_tc_conv_staged<64><<<grid, TC_THREADS, smem, s>>>(a); break;
-        case 128: k_tc_conv_staged<128><<<grid, TC_THREADS, smem, s>>>(a); break;
-        default: k_tc_conv_staged<256><<<grid, TC_THREADS, smem, s>>>(a); break;
+        case 32: if (a.up) launch_k(k_tc_conv_staged<32, true>, dim3(grid), dim3(TC_THREADS), smem, s, a); else launch_k(k_tc_conv_staged<32, false>, dim3(grid), dim3(TC_THREADS), smem, s, a); break;
+        case 64: if (a.up) launch_k(k_tc_conv_staged<64, true>, dim3(grid), dim3(TC_THREADS), smem, s, a); else launch_k(k_tc_conv_staged<64, false>, dim3(grid), dim3(TC_THREADS), smem, s, a); break;
+        case 128: if (a.up) launch_k(k_tc_conv_staged<128, true>, dim3(grid), dim3(TC_THREADS), smem, s, a); else launch_k(k_tc_conv_staged<128, false>, dim3(grid), dim3(TC_THREADS), smem, s, a); break;
+        default: if (a.up) launch_k(k_tc_conv_staged<256, true>, dim3(grid), dim3(TC_THREADS), smem, s, a); else launch_k(k_tc_conv_staged<256, false>, dim3(grid), dim3(TC_THREADS), smem, s, a); break;
     }
 }
 void launch_tc_dwpw(const TcDwArgs &a, int nsplit, cudaStream_t s) {
@@ -232,17 +237,18 @@ void launch_tc_dwpw(const TcDwArgs &a, int nsplit, cudaStream_t s) {
     dim3 grid((unsigned)((M + a.rows - 1) / a.rows), nsplit);
     const size_t smem = tc_dw_smem_bytes(a);
     switch (tc_tmem_cols(a.N)) {
-        case 32: k_tc_dwpw_staged<32><<<grid, TC_THREADS, smem, s>>>(a); break;
-        case 64: k_tc_dwpw_staged<64><<<grid, TC_THREADS, smem, s>>>(a); break;
-        case 128: k_tc_dwpw_staged<128><<<grid, TC_THREADS, smem, s>>>(a); break;
-        default: k_tc_dwpw_staged<256><<<grid, TC_THREADS, smem, s>>>(a); break;
+        case 32: launch_k(k_tc_dwpw_staged<32>, grid, dim3(TC_THREADS), smem, s, a); break;
+        case 64: launch_k(k_tc_dwpw_staged<64>, grid, dim3(TC_THREADS), smem, s, a); break;
+        case 128: launch_k(k_tc_dwpw_staged<128>, grid, dim3(TC_THREADS), smem, s, a); break;
+        default: launch_k(k_tc_dwpw_staged<256>, grid, dim3(TC_THREADS), smem, s, a); break;
     }
 }
 constexpr int TC_SMEM_LIMIT = 200 * 1024;   // dynamic; the kernels also hold ~20 KB static
 cudaError_t tc_init() {
     cudaError_t e;
 #define RF_TC_ATTR(K_) if ((e = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT))) return e
-    RF_TC_ATTR(k_tc_conv_staged<32>); RF_TC_ATTR(k_tc_conv_staged<64>); RF_TC_ATTR(k_tc_conv_staged<128>); RF_TC_ATTR(k_tc_conv_staged<256>);
+    RF_TC_ATTR((k_tc_conv_staged<32, false>)); RF_TC_ATTR((k_tc_conv_staged<64, false>)); RF_TC_ATTR((k_tc_conv_staged<128, false>)); RF_TC_ATTR((k_tc_conv_staged<256, false>));
+    RF_TC_ATTR((k_tc_conv_staged<32, true>)); RF_TC_ATTR((k_tc_conv_staged<64, true>)); RF_TC_ATTR((k_tc_conv_staged<128, true>)); RF_TC_ATTR((k_tc_conv_staged<256, true>));
     RF_TC_ATTR(k_tc_dwpw_staged<32>); RF_TC_ATTR(k_tc_dwpw_staged<64>); RF_TC_ATTR(k_tc_dwpw_staged<128>); RF_TC_ATTR(k_tc_dwpw_staged<256>);
 #undef RF_TC_ATTR
     return cudaSuccess;
@@ -304,7 +310,7 @@ void build_plan(rf_handle h) {
         s.bytes_per_img = (double)H * W * 3 + (double)cur_h * cur_w * 8 * es;
         s.launch = [=](int n, cudaStream_t st) {
             long total = (long)n * (H / 2) * (W / 2);
-            k_conv0<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->d_params, T_(out), Wd(ow), Wd(ob), n, H, W);
+            launch_k(k_conv0<T>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const PostParams *)h->d_params, T_(out), Wd(ow), Wd(ob), n, H, W);
         };
         B.step(std::move(s));
     }
@@ -361,8 +367,8 @@ void build_plan(rf_handle h) {
             s.launch = [=](int n, cudaStream_t st) {
                 long total = (long)n * oh * ow_ * (C / 8);
                 unsigned g = (unsigned)((total + 255) / 256);
-                if (S == 1) k_dw3x3<T, 1><<<g, 256, 0, st>>>(T_(tin), T_(tdw), Wd(owd), Wd(obd), n, ih, iw, C);
-                else k_dw3x3<T, 2><<<g, 256, 0, st>>>(T_(tin), T_(tdw), Wd(owd), Wd(obd), n, ih, iw, C);
+                if (S == 1) launch_k(k_dw3x3<T, 1>, dim3(g), dim3(256), 0, st, (const T *)T_(tin), T_(tdw), Wd(owd), Wd(obd), n, ih, iw, C);
+                else launch_k(k_dw3x3<T, 2>, dim3(g), dim3(256), 0, st, (const T *)T_(tin), T_(tdw), Wd(owd), Wd(obd), n, ih, iw, C);
             };
             B.step(std::move(s));
         }
@@ -392,7 +398,8 @@ void build_plan(rf_handle h) {
 
     // ---- FPN + SSH (prototxt:1199-2302) -----------------------------------------------------
     auto conv_step = [&](const std::string &sname, std::vector<const FoldedConv *> cs, int tin, int ih, int iw,
-                         int t0, int ld0, int off0, int n0, int relu0, int t1, int ld1, int off1, int relu1) {
+                         int t0, int ld0, int off0, int n0, int relu0, int t1, int ld1, int off1, int relu1, int lane = 0,
+                         int tup = -1, int up_which = 0) {
         if constexpr (std::is_same<T, __half>::value) {
             if (h->use_tc) {
                 std::vector<float> bias;
@@ -400,13 +407,16 @@ void build_plan(rf_handle h) {
                 std::vector<__half> img = pack_tc_weights(cs, bias, Kpad);
                 size_t oimg = B.add_weights_h(img), ob = B.add_weights(bias);
                 const int N = (int)bias.size(), cin = cs[0]->cin, ks = cs[0]->k;
+                size_t oup = tup >= 0 ? B.add_weights(m.up_w[up_which]) : 0;
                 Step s;
                 s.name = "tc_" + sname;
+                s.lane = lane;
                 s.in = {tin};
+                if (tup >= 0) s.in.push_back(tup);
                 s.out = {t0};
                 if (t1 >= 0) s.out.push_back(t1);
-                s.flops_per_img = 2.0 * ih * iw * cin * ks * ks * N;
-                s.bytes_per_img = ((double)ih * iw * cin + (double)ih * iw * N) * es;
+                s.flops_per_img = 2.0 * ih * iw * cin * ks * ks * N + (tup >= 0 ? 2.0 * ih * iw * cin * 4 : 0.0);
+                s.bytes_per_img = ((double)ih * iw * cin + (double)ih * iw * N + (tup >= 0 ? (double)(ih / 2) * (iw / 2) * cin : 0.0)) * es;
                 s.launch = [=](int n, cudaStream_t st) {
                     TcConvArgs a{};
                     a.in = T_(tin); a.Cin = cin; a.nimg = n; a.H = ih; a.W = iw; a.taps = ks * ks; a.N = N;
@@ -414,6 +424,7 @@ void build_plan(rf_handle h) {
                     a.R = (ks == 3 ? 128 + 2 * (iw + 3) : 128) | 1;
                     a.wimg = h->d_weights_h + oimg; a.bias = Wd(ob);
                     a.out = TcOut{T_(t0) + off0, ld0, n0, relu0, t1 >= 0 ? T_(t1) + off1 : nullptr, ld1, relu1};
+                    if (tup >= 0) { a.up = T_(tup); a.up_w = Wd(oup); }
                     launch_tc_conv(a, st);
                 };
                 B.step(std::move(s));
@@ -427,6 +438,7 @@ void build_plan(rf_handle h) {
         const int ldin = h->tensors[tin].c;
         Step s;
         s.name = sname;
+        s.lane = lane;
         s.in = {tin};
         s.out = {t0};
         if (t1 >= 0) s.out.push_back(t1);
@@ -438,20 +450,20 @@ void build_plan(rf_handle h) {
         };
         B.step(std::move(s));
     };
-    auto ssh = [&](const std::string &lvname, int tin, int fh, int fw, int level) {
+    auto ssh = [&](const std::string &lvname, int tin, int fh, int fw, int level, int lane) {
         const std::string p = "rf_" + lvname + "_det";
         int cat = B.tensor(p + "_concat_relu", fh, fw, 64);
         int ctx1 = B.tensor(p + "_context_conv1_relu", fh, fw, 16);
         int ctx31 = B.tensor(p + "_context_conv3_1_relu", fh, fw, 16);
         // det_conv1 (64->32, BN, ReLU after concat) + context_conv1 (64->16, BN, ReLU): one launch
         conv_step("ssh_" + lvname + "_conv1+ctx1_3x3_64to48", {&m.conv(p + "_conv1"), &m.conv(p + "_context_conv1")}, tin, fh,
-                  fw, cat, 64, 0, 32, 1, ctx1, 16, 0, 1);
+                  fw, cat, 64, 0, 32, 1, ctx1, 16, 0, 1, lane);
         // context_conv2 (16->16 -> concat[32:48]) + context_conv3_1 (16->16, ReLU): one launch
         conv_step("ssh_" + lvname + "_ctx2+ctx3_1_3x3_16to32", {&m.conv(p + "_context_conv2"), &m.conv(p + "_context_conv3_1")},
-                  ctx1, fh, fw, cat, 64, 32, 16, 1, ctx31, 16, 0, 1);
+                  ctx1, fh, fw, cat, 64, 32, 16, 1, ctx31, 16, 0, 1, lane);
         // context_conv3_2 (16->16 -> concat[48:64])
         conv_step("ssh_" + lvname + "_ctx3_2_3x3_16to16", {&m.conv(p + "_context_conv3_2")}, ctx31, fh, fw, cat, 64, 48, 16, 1,
-                  -1, 0, 0, 0);
+                  -1, 0, 0, 0, lane);
         h->feat_tensor[level] = cat;
         // the concat tensor is written by three steps: make it live from the first of them
     };
@@ -465,28 +477,54 @@ void build_plan(rf_handle h) {
         s.bytes_per_img = ((double)fh * fw * 64 * 2 + (double)(fh / 2) * (fw / 2) * 64) * es;
         s.launch = [=](int n, cudaStream_t st) {
             long total = (long)n * fh * fw * 8;
-            k_upsample_add<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(T_(tlat), T_(tup), T_(out), Wd(ow), n, fh, fw, 64,
-                                                                           fh / 2, fw / 2);
+            launch_k(k_upsample_add<T>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const T *)T_(tlat), (const T *)T_(tup), T_(out), Wd(ow), n,
+                     fh, fw, 64, fh / 2, fw / 2);
         };
         B.step(std::move(s));
         return out;
     };
     const int h32 = H / 32, w32 = W / 32, h16 = H / 16, w16 = W / 16, h8 = H / 8, w8 = W / 8;
+    // Lanes: the forward graph is not a chain.  rf_c1_red_conv only needs C1 and rf_c2_lateral only C2,
+    // so they run on side lanes while the backbone continues; each level's SSH head runs on a side lane
+    // while the main lane walks the top-down path lat3 -> aggr2 -> aggr1 -> ssh_c1 (the critical path).
+    // In TC mode the FPN merge (deconv-upsample + add) is fused into the aggr conv's staging.
+    const bool lanes = h->use_tc;
+    // A side-lane step may start as soon as its producer finishes, i.e. EARLIER than later main-lane steps:
+    // the step list (which the arena's liveness analysis walks in order) must show it right after that
+    // producer, otherwise its output could be placed on memory a concurrently running main step still uses.
+    auto move_last_step_after_producer = [&](int tensor_id) {
+        int pos = 0;
+        for (int i = (int)h->steps.size() - 2; i >= 0 && !pos; i--)
+            for (int t : h->steps[i].out) if (t == tensor_id) { pos = i + 1; break; }
+        Step st = std::move(h->steps.back());
+        h->steps.pop_back();
+        h->steps.insert(h->steps.begin() + pos, std::move(st));
+    };
     int lat3 = B.tensor("rf_c3_lateral_relu", h32, w32, 64);
-    conv_step("c3_lateral_1x1_256to64", {&m.conv("rf_c3_lateral")}, c3, h32, w32, lat3, 64, 0, 64, 1, -1, 0, 0, 0);
-    ssh("c3", lat3, h32, w32, 0);
     int lat2 = B.tensor("rf_c2_lateral_relu", h16, w16, 64);
-    conv_step("c2_lateral_1x1_128to64", {&m.conv("rf_c2_lateral")}, c2, h16, w16, lat2, 64, 0, 64, 1, -1, 0, 0, 0);
-    int plus0 = upadd("_plus0", lat2, lat3, h16, w16, 0);
-    int aggr2 = B.tensor("rf_c2_aggr_relu", h16, w16, 64);
-    conv_step("c2_aggr_3x3_64to64", {&m.conv("rf_c2_aggr")}, plus0, h16, w16, aggr2, 64, 0, 64, 1, -1, 0, 0, 0);
-    ssh("c2", aggr2, h16, w16, 1);
     int lat1 = B.tensor("rf_c1_red_conv_relu", h8, w8, 64);
-    conv_step("c1_red_1x1_64to64", {&m.conv("rf_c1_red_conv")}, c1, h8, w8, lat1, 64, 0, 64, 1, -1, 0, 0, 0);
-    int plus1 = upadd("_plus1", lat1, aggr2, h8, w8, 1);
+    conv_step("c1_red_1x1_64to64", {&m.conv("rf_c1_red_conv")}, c1, h8, w8, lat1, 64, 0, 64, 1, -1, 0, 0, 0, lanes ? 1 : 0);
+    if (lanes) move_last_step_after_producer(c1);
+    conv_step("c2_lateral_1x1_128to64", {&m.conv("rf_c2_lateral")}, c2, h16, w16, lat2, 64, 0, 64, 1, -1, 0, 0, 0, lanes ? 2 : 0);
+    if (lanes) move_last_step_after_producer(c2);
+    conv_step("c3_lateral_1x1_256to64", {&m.conv("rf_c3_lateral")}, c3, h32, w32, lat3, 64, 0, 64, 1, -1, 0, 0, 0);
+    ssh("c3", lat3, h32, w32, 0, lanes ? 1 : 0);
+    int aggr2 = B.tensor("rf_c2_aggr_relu", h16, w16, 64);
+    if (h->use_tc) {
+        conv_step("c2_upsample+add+aggr_3x3_64to64", {&m.conv("rf_c2_aggr")}, lat2, h16, w16, aggr2, 64, 0, 64, 1, -1, 0, 0, 0, 0, lat3, 0);
+    } else {
+        int plus0 = upadd("_plus0", lat2, lat3, h16, w16, 0);
+        conv_step("c2_aggr_3x3_64to64", {&m.conv("rf_c2_aggr")}, plus0, h16, w16, aggr2, 64, 0, 64, 1, -1, 0, 0, 0);
+    }
+    ssh("c2", aggr2, h16, w16, 1, lanes ? 2 : 0);
     int aggr1 = B.tensor("rf_c1_aggr_relu", h8, w8, 64);
-    conv_step("c1_aggr_3x3_64to64", {&m.conv("rf_c1_aggr")}, plus1, h8, w8, aggr1, 64, 0, 64, 1, -1, 0, 0, 0);
-    ssh("c1", aggr1, h8, w8, 2);
+    if (h->use_tc) {
+        conv_step("c1_upsample+add+aggr_3x3_64to64", {&m.conv("rf_c1_aggr")}, lat1, h8, w8, aggr1, 64, 0, 64, 1, -1, 0, 0, 0, 0, aggr2, 1);
+    } else {
+        int plus1 = upadd("_plus1", lat1, aggr2, h8, w8, 1);
+        conv_step("c1_aggr_3x3_64to64", {&m.conv("rf_c1_aggr")}, plus1, h8, w8, aggr1, 64, 0, 64, 1, -1, 0, 0, 0);
+    }
+    ssh("c1", aggr1, h8, w8, 2, 0);
 
     // ---- predictors + decode (fused) and NMS -------------------------------------------------
     size_t hw_off[3], hb_off[3];
@@ -532,13 +570,47 @@ void build_plan(rf_handle h) {
     }
 }
 
-// Liveness-based first-fit placement of activation tensors in one arena.
+// Cross-lane dependencies: a step waits (event) for the producers of its inputs that live in another lane.
+void link_steps(rf_handle h) {
+    auto &st = h->steps;
+    for (int i = 0; i < (int)st.size(); i++) {
+        st[i].deps.clear();
+        for (int t : st[i].in) {
+            for (int j = i - 1; j >= 0; j--) {
+                bool writes = false;
+                for (int o : st[j].out) writes |= (o == t);
+                if (!writes) continue;
+                if (st[j].lane != st[i].lane) {
+                    if (std::find(st[i].deps.begin(), st[i].deps.end(), j) == st[i].deps.end()) st[i].deps.push_back(j);
+                    st[j].signals = true;
+                }
+                break;   // the last writer before i (its lane orders earlier writers of the same tensor)
+            }
+        }
+    }
+}
+
+// Liveness-based first-fit placement of activation tensors in one arena.  Steps on side lanes run
+// concurrently with later main-lane steps: every tensor such a step touches stays live until the
+// first step of another lane that waits for its lane (the join), so no concurrent writer can land on it.
 void place_tensors(rf_handle h, bool keep_all) {
     auto &ts = h->tensors;
-    for (int si = 0; si < (int)h->steps.size(); si++) {
-        for (int t : h->steps[si].out) { if (ts[t].first < 0) ts[t].first = si; ts[t].last = std::max(ts[t].last, si); }
-        for (int t : h->steps[si].in) ts[t].last = std::max(ts[t].last, si);
+    auto &st = h->steps;
+    for (int si = 0; si < (int)st.size(); si++) {
+        for (int t : st[si].out) { if (ts[t].first < 0) ts[t].first = si; ts[t].last = std::max(ts[t].last, si); }
+        for (int t : st[si].in) ts[t].last = std::max(ts[t].last, si);
     }
+    for (int k = 0; k < (int)st.size(); k++) {
+        if (st[k].lane == 0) continue;
+        int join = (int)st.size() - 1;
+        for (int j = k + 1; j < (int)st.size() && join == (int)st.size() - 1; j++)
+            for (int d : st[j].deps)
+                if (st[j].lane != st[k].lane && st[d].lane == st[k].lane && d >= k) { join = j; break; }
+        for (int t : st[k].in) ts[t].last = std::max(ts[t].last, join);
+        for (int t : st[k].out) ts[t].last = std::max(ts[t].last, join);
+    }
+    // a main-lane step that runs while a side lane is still reading must not overwrite those inputs either:
+    // covered above because the side step's inputs stay live until the join.
     const size_t B = (size_t)h->cfg.max_batch;
     size_t top = 0;
     std::vector<int> order(ts.size());
@@ -569,8 +641,17 @@ void place_tensors(rf_handle h, bool keep_all) {
     h->arena_bytes = top;
 }
 
-void run_steps(rf_handle h, int n, cudaStream_t s) {
-    for (auto &st : h->steps) st.launch(n, s);
+// Issue the forward pass: lane 0 on `s`, side lanes on their own streams, joined by events.  Works both
+// under stream capture (the side streams fork from / join into the capturing stream) and eagerly.
+void run_steps(rf_handle h, int n, cudaStream_t s, bool use_lanes = true) {
+    for (size_t i = 0; i < h->steps.size(); i++) {
+        Step &st = h->steps[i];
+        cudaStream_t cs = (use_lanes && st.lane) ? h->lane_stream[st.lane] : s;
+        if (use_lanes)
+            for (int d : st.deps) CK(cudaStreamWaitEvent(cs, h->step_event[d], 0));
+        st.launch(n, cs);
+        if (use_lanes && st.signals) CK(cudaEventRecord(h->step_event[i], cs));
+    }
 }
 
 void forward_graph(rf_handle h, int n) {
@@ -617,6 +698,8 @@ void destroy(rf_handle h) {
     cudaFree(h->pb.flag_scratch); cudaFree(h->pb.out_dets); cudaFree(h->pb.out_counts); cudaFree(h->pb.out_total_kept);
     for (auto p : h->d_blobs) cudaFree(p);
     cudaFreeHost(h->h_input); cudaFreeHost(h->h_raw); cudaFreeHost(h->h_params); cudaFreeHost(h->h_dets); cudaFreeHost(h->h_counts);
+    for (auto e : h->step_event) if (e) cudaEventDestroy(e);
+    for (int l = 1; l < 3; l++) if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -729,6 +812,11 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
         h->use_tc = h->cfg.precision == RF_PREC_FP16 && !(h->cfg.flags & RF_FLAG_NO_TENSORCORE);
         if (h->use_tc) CK(tc_init());
         if (h->cfg.precision == RF_PREC_FP32) build_plan<float>(h); else build_plan<__half>(h);
+        link_steps(h);
+        for (int l = 1; l < 3; l++) CK(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
+        h->step_event.resize(h->steps.size(), nullptr);
+        for (size_t i = 0; i < h->steps.size(); i++)
+            if (h->steps[i].signals) CK(cudaEventCreateWithFlags(&h->step_event[i], cudaEventDisableTiming));
         place_tensors(h, false);
         CK(cudaMalloc(&h->arena, h->arena_bytes));
         CK(cudaMalloc(&h->d_weights, h->wstage.size() * sizeof(float)));
@@ -1040,7 +1128,7 @@ int rf_profile_layers(rf_handle h, int n, int iters, char (*names)[64], float *m
     try {
         CK(cudaSetDevice(h->device));
         set_params(h, h->cur_thr, h->cur_nms);
-        run_steps(h, n, h->stream);  // warm everything once (also leaves consistent inputs for every step)
+        run_steps(h, n, h->stream, false);  // warm everything once (also leaves consistent inputs for every step)
         CK(cudaStreamSynchronize(h->stream));
         for (size_t si = 0; si < h->steps.size(); si++) {
             auto &st = h->steps[si];

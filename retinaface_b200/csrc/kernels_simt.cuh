@@ -22,8 +22,10 @@ __global__ void __launch_bounds__(256) k_conv0(const PostParams *__restrict__ ru
                                                const float *__restrict__ wk, const float *__restrict__ bias,
                                                int n, int H, int W) {
     __shared__ float sw[27 * 8 + 8];
+    pdl_trigger();
     for (int i = threadIdx.x; i < 27 * 8 + 8; i += blockDim.x) sw[i] = i < 216 ? wk[i] : bias[i - 216];
     __syncthreads();
+    pdl_wait();
     const int OH = H >> 1, OW = W >> 1;
     const long total = (long)n * OH * OW;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,6 +71,8 @@ template <typename T, int STRIDE>
 __global__ void __launch_bounds__(256) k_dw3x3(const T *__restrict__ in, T *__restrict__ out,
                                                const float *__restrict__ wd, const float *__restrict__ bias,
                                                int n, int H, int W, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int OH = H / STRIDE, OW = W / STRIDE;
     const int cg = C >> 3;
     const long total = (long)n * OH * OW * cg;
@@ -130,6 +134,8 @@ __global__ void __launch_bounds__(256) k_conv_gemm(const T *__restrict__ in, int
                                                    const float *__restrict__ wk, const float *__restrict__ bias,
                                                    int N, OutSplit<T> outs, int nimg, int H, int W) {
     constexpr int BM = 64, BK = 16, TN = BN / 16;
+    pdl_trigger();
+    pdl_wait();
     __shared__ float As[BK][BM + 2];
     __shared__ float Bs[BK][BN];
     const int tid = threadIdx.x;
@@ -220,6 +226,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_upsample_add(const T *__restrict__ lateral, const T *__restrict__ up,
                                                       T *__restrict__ out, const float *__restrict__ uw,
                                                       int n, int H, int W, int C, int UH, int UW) {
+    pdl_trigger();
+    pdl_wait();
     const int cg = C >> 3;
     const long total = (long)n * H * W * cg;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -91,9 +91,11 @@ __global__ void __launch_bounds__(128) k_head_decode(HeadLaunch L, int net_w, in
     const int blk = blockIdx.x;
     const int l = blk >= L.blk_base[2] ? 2 : (blk >= L.blk_base[1] ? 1 : 0);
     const LevelDesc lv = L.lv[l];
-    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) sw[i] = L.hw[l].w[i];
+    pdl_trigger();
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) sw[i] = L.hw[l].w[i];   // weights: independent of the previous kernel
     if (threadIdx.x < 32) sb[threadIdx.x] = L.hw[l].b[threadIdx.x];
     __syncthreads();
+    pdl_wait();
     const int hw = lv.h * lv.w;
     const int j = (blk - L.blk_base[l]) * blockDim.x + threadIdx.x;
     if (j >= hw) return;
@@ -171,6 +173,8 @@ struct BlobLaunch {
 // rf_postprocess: one thread per anchor, reading caller-supplied NCHW head blobs.
 __global__ void __launch_bounds__(256) k_blob_decode(BlobLaunch L, int net_w, int net_h,
                                                      const PostParams *__restrict__ params, PostBuffers pb) {
+    pdl_trigger();
+    pdl_wait();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;  // emission index within the image
     if (e >= pb.anchors_per_image) return;
     const int img = blockIdx.y;
@@ -213,6 +217,8 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms(const PostParams *__restric
     const int img = blockIdx.x;
     const int tid = threadIdx.x;
     const int A = pb.anchors_per_image;
+    pdl_trigger();
+    pdl_wait();
     int n = pb.cand_count[img];
     if (n > A) n = A;
     int np2 = 1;
@@ -317,8 +323,8 @@ void launch_head_decode(const T *const feat[3], const HeadWeights hw[3], const L
     L.blk_base[3] = blk;
     for (int i = 0; i < 9; i++) L.blobs[i] = write ? blobs[i] : nullptr;
     dim3 grid(blk, n);
-    if (write) k_head_decode<T, true><<<grid, 128, 0, s>>>(L, net_w, net_h, params, pb);
-    else k_head_decode<T, false><<<grid, 128, 0, s>>>(L, net_w, net_h, params, pb);
+    if (write) launch_k(k_head_decode<T, true>, grid, dim3(128), 0, s, L, net_w, net_h, params, pb);
+    else launch_k(k_head_decode<T, false>, grid, dim3(128), 0, s, L, net_w, net_h, params, pb);
 }
 template void launch_head_decode<float>(const float *const[3], const HeadWeights[3], const LevelDesc[3], int, int, int,
                                         const PostParams *, const PostBuffers &, float *const[9], cudaStream_t);
@@ -331,11 +337,11 @@ void launch_blob_decode(const float *const blobs[9], const LevelDesc lv[3], int 
     for (int i = 0; i < 9; i++) L.blobs[i] = blobs[i];
     for (int l = 0; l < 3; l++) L.lv[l] = lv[l];
     dim3 grid((pb.anchors_per_image + 255) / 256, n);
-    k_blob_decode<<<grid, 256, 0, s>>>(L, net_w, net_h, params, pb);
+    launch_k(k_blob_decode, grid, dim3(256), 0, s, L, net_w, net_h, params, pb);
 }
 
 void launch_nms(int n, const PostParams *params, const PostBuffers &pb, cudaStream_t s) {
-    k_nms<<<n, NMS_THREADS, nms_smem_bytes(pb.max_faces), s>>>(params, pb);
+    launch_k(k_nms, dim3(n), dim3(NMS_THREADS), nms_smem_bytes(pb.max_faces), s, params, pb);
 }
 
 cudaError_t postproc_init() {

@@ -138,6 +138,10 @@ struct TcConvArgs {
     const __half *wimg;     // B image [K/8][N][8] halfs, K = taps*Cin ordered (tap, cin)
     const float *bias;      // [N]
     TcOut out;
+    // FPN merge fused into the staging (template UPADD): in := in + crop(deconv_k4s2p1(up)) -- the
+    // Eltwise SUM of prototxt:1585 / :1980 never exists as a tensor.  up: [nimg][H/2][W/2][Cin], up_w: [Cin][16].
+    const __half *up;
+    const float *up_w;
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, bool valid) {
@@ -150,8 +154,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 // Epilogue shared by both kernels: 8 warps; warp w reads TMEM lane quadrant (w & 3) and the 16-column
 // blocks j with (j & 1) == (w >> 2); thread = one GEMM row.
-__device__ __forceinline__ void tc_epilogue(uint32_t tmem, int N, const float *__restrict__ bias, const TcOut &o, long out_row,
-                                            int n_off) {
+__device__ __forceinline__ void tc_epilogue(uint32_t tmem, int N, const float *s_bias /* smem, this CTA's N channels */, const TcOut &o,
+                                            long out_row, int n_off) {
     const int warp = threadIdx.x >> 5;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     for (int j = warp >> 2; j < (N >> 4); j += 2) {
@@ -167,7 +171,7 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, int N, const float *_
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                f[i] = __uint_as_float(r[i]) + __ldg(bias + gn + i);
+                f[i] = __uint_as_float(r[i]) + s_bias[n0 + i];
                 if (relu) f[i] = fmaxf(f[i], 0.f);
             }
             Vec8<__half> o0, o1;
@@ -183,12 +187,14 @@ inline size_t tc_conv_smem_bytes(const TcConvArgs &a) {
     return (size_t)(a.Cin / 8) * a.R * 16 + (size_t)a.taps * a.Cin * a.N * 2 + 128;
 }
 
-template <int NT>
+template <int NT, bool UPADD>
 __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_b, bar_done;
     __shared__ uint32_t s_tmem;
     __shared__ int s_off[TC_MAX_R];      // staged position -> element offset of its pixel in `in`, -1 = zero padding
+    __shared__ float s_bias[256];
+    __shared__ float s_uw[UPADD ? 64 * 16 : 1];
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int pad = a.taps == 9 ? 1 : 0;
@@ -209,6 +215,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
         tc::bulk_g2s(sB, a.wimg, bytes, &bar_b);     // all taps' weights: one TMA bulk copy
     }
     if (warp == 1) tc::tmem_alloc<NT>(&s_tmem);
+    pdl_trigger();
+    if (tid < a.N) s_bias[tid] = a.bias[tid];
+    if (UPADD) for (int i = tid; i < a.Cin * 16; i += TC_THREADS) s_uw[i] = a.up_w[i];
     for (int pl = tid; pl < a.R; pl += TC_THREADS) {
         const long p = lo + pl;
         int off = -1;
@@ -221,13 +230,54 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
         s_off[pl] = off;
     }
     __syncthreads();
+    pdl_wait();                          // everything above is independent of the previous kernel's output
     // ---- stage the range: item = (position, 8-channel group), 16 B each --------------------------------
-    for (int it = tid; it < a.R * G; it += TC_THREADS) {
-        const int g = it % G, pl = it / G;
-        const int off = s_off[pl];
-        cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (off >= 0 ? off + g * 8 : 0), off >= 0);
+    if (!UPADD) {
+        for (int it = tid; it < a.R * G; it += TC_THREADS) {
+            const int g = it % G, pl = it / G;
+            const int off = s_off[pl];
+            cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (off >= 0 ? off + g * 8 : 0), off >= 0);
+        }
+        cp_async_wait_all();
+    } else {
+        // lateral + bilinear-deconv(up): same operation order as k_upsample_add (kernels_simt.cuh), so the
+        // staged FP16 values equal the ones the unfused Eltwise tensor would hold.
+        const int UH = a.H >> 1, UW = a.W >> 1;
+        for (int it = tid; it < a.R * G; it += TC_THREADS) {
+            const int g = it % G, pl = it / G;
+            const int off = s_off[pl];
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (off >= 0) {
+                const int pix = off / a.Cin, c0 = g * 8;
+                const int x = pix % a.W, y = (pix / a.W) % a.H, b = pix / (a.W * a.H);
+                Vec8<__half> lv;
+                lv.load(a.in + off + c0);
+                float acc[8];
+                lv.to_float(acc);
+                const int i_hi = (y + 1) >> 1, j_hi = (x + 1) >> 1;
+#pragma unroll
+                for (int di = 0; di < 2; di++) {
+                    const int i = i_hi - di, ky = y - 2 * i + 1;
+                    if (i < 0 || i >= UH || ky < 0 || ky > 3) continue;
+#pragma unroll
+                    for (int dj = 0; dj < 2; dj++) {
+                        const int j = j_hi - dj, kx = x - 2 * j + 1;
+                        if (j < 0 || j >= UW || kx < 0 || kx > 3) continue;
+                        Vec8<__half> uv;
+                        uv.load(a.up + (((size_t)b * UH + i) * UW + j) * a.Cin + c0);
+                        float f[8];
+                        uv.to_float(f);
+#pragma unroll
+                        for (int c = 0; c < 8; c++) acc[c] = fmaf(f[c], s_uw[(c0 + c) * 16 + ky * 4 + kx], acc[c]);
+                    }
+                }
+                Vec8<__half> o;
+                o.from_float(acc);
+                v = o.v;
+            }
+            *reinterpret_cast<uint4 *>(sS + (size_t)g * lbo_s + (size_t)pl * 16) = v;
+        }
     }
-    cp_async_wait_all();
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -259,7 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     {
         const int r = (warp & 3) * 32 + (tid & 31);
         const int off = s_off[(int)(m0 - lo) + r];               // element offset / Cin == output pixel index
-        tc_epilogue(tmem, a.N, a.bias, a.out, off >= 0 ? (long)(off / a.Cin) : -1, 0);
+        tc_epilogue(tmem, a.N, s_bias, a.out, off >= 0 ? (long)(off / a.Cin) : -1, 0);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -300,10 +350,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
     __shared__ uint32_t s_tmem;
     __shared__ int s_off[TC_MAX_R];
     __shared__ int s_cpos[128];          // GEMM row -> staged index of its stencil centre, -1 = no output
-    __shared__ float s_dw[10 * 256];
+    __shared__ float s_bias[256];
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int G = a.C >> 3;
+    const int GA = a.Kpad >> 3;          // A groups (== G except the Cin = 8 layer: 2, second one zero)
+    const int g_own = tid % GA;
     const uint32_t lbo_s = (uint32_t)a.Rmax * 16;
     unsigned char *sS = smem;
     unsigned char *sA = smem + (size_t)G * lbo_s;
@@ -329,8 +381,18 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
         tc::bulk_g2s(sB, a.wimg + (size_t)blockIdx.y * a.Kpad * a.N, bytes, &bar_b);
     }
     if (warp == 1) tc::tmem_alloc<NT>(&s_tmem);
-    for (int i = tid; i < 9 * a.C; i += TC_THREADS) s_dw[i] = a.dw_w[i];
-    for (int i = tid; i < a.C; i += TC_THREADS) s_dw[9 * 256 + i] = a.dw_b[i];
+    pdl_trigger();
+    if (tid < a.N) s_bias[tid] = a.bias[blockIdx.y * a.N + tid];
+    float wreg[10][8];                   // [tap][channel] folded depthwise weights, [9] = bias
+    if (g_own < G) {
+#pragma unroll
+        for (int t = 0; t < 10; t++) {
+            const float *src = (t < 9 ? a.dw_w + t * a.C : a.dw_b) + g_own * 8;
+            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(src)), w1 = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+            wreg[t][0] = w0.x; wreg[t][1] = w0.y; wreg[t][2] = w0.z; wreg[t][3] = w0.w;
+            wreg[t][4] = w1.x; wreg[t][5] = w1.y; wreg[t][6] = w1.z; wreg[t][7] = w1.w;
+        }
+    }
     for (int pl = tid; pl < R; pl += TC_THREADS) {
         const long p = lo + pl;
         int off = -1;
@@ -347,6 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
         s_cpos[tid] = (tid < a.rows && m < M) ? (int)(centre(m) - lo) : -1;
     }
     __syncthreads();
+    pdl_wait();
     for (int it = tid; it < R * G; it += TC_THREADS) {
         const int g = it % G, pl = it / G;
         const int off = s_off[pl];
@@ -355,17 +418,16 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
     cp_async_wait_all();
     __syncthreads();
     // ---- depthwise stencil from shared memory -> A operand (canonical K-major layout) -------------------
-    const int GA = a.Kpad >> 3;          // A groups (== G except the Cin = 8 layer: 2, second one zero)
-    for (int it = tid; it < 128 * GA; it += TC_THREADS) {
-        const int g = it % GA, r = it / GA;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        const int cp = s_cpos[r];
-        if (cp >= 0 && g < G) {
-            const int c0 = g * 8;
+    // Each thread owns ONE 8-channel group (TC_THREADS % GA == 0) and walks the tile's rows, so its 72
+    // folded depthwise weights + 8 biases live in registers (loaded before pdl_wait, above).
+    if (g_own < G) {
+        for (int r = tid / GA; r < a.rows; r += TC_THREADS / GA) {
+            const int cp = s_cpos[r];
+            if (cp < 0) continue;            // rows beyond M (last tile): never read back
             float acc[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] = s_dw[9 * 256 + c0 + i];
-            const unsigned char *base = sS + (size_t)g * lbo_s + (size_t)cp * 16;
+            for (int i = 0; i < 8; i++) acc[i] = wreg[9][i];
+            const unsigned char *base = sS + (size_t)g_own * lbo_s + (size_t)cp * 16;
 #pragma unroll
             for (int t = 0; t < 9; t++) {
                 const int shift = (t / 3 - 1) * a.Wp + (t % 3 - 1);
@@ -373,17 +435,18 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
                 x.v = *reinterpret_cast<const uint4 *>(base + shift * 16);
                 float f[8];
                 x.to_float(f);
-                const float *wr = &s_dw[t * a.C + c0];
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] = fmaf(f[i], wr[i], acc[i]);
+                for (int i = 0; i < 8; i++) acc[i] = fmaf(f[i], wreg[t][i], acc[i]);
             }
 #pragma unroll
             for (int i = 0; i < 8; i++) acc[i] = fmaxf(acc[i], 0.f);
             Vec8<__half> o;
             o.from_float(acc);
-            v = o.v;
+            *reinterpret_cast<uint4 *>(sA + (size_t)g_own * TC_LBO_A + (size_t)r * 16) = o.v;
         }
-        *reinterpret_cast<uint4 *>(sA + (size_t)g * TC_LBO_A + (size_t)r * 16) = v;
+    } else {                                  // K padding group of the Cin = 8 layer: zeros
+        for (int r = tid / GA; r < a.rows; r += TC_THREADS / GA)
+            *reinterpret_cast<uint4 *>(sA + (size_t)g_own * TC_LBO_A + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
@@ -409,7 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
         const int r = (warp & 3) * 32 + (tid & 31);
         const long m = m0 + r;
         TcOut o{a.out, a.Ntotal, a.Ntotal, 1, nullptr, 0, 0};
-        tc_epilogue(tmem, a.N, a.bias, o, (r < a.rows && m < M) ? m : -1, (int)blockIdx.y * a.N);
+        tc_epilogue(tmem, a.N, s_bias, o, (r < a.rows && m < M) ? m : -1, (int)blockIdx.y * a.N);
     }
     tc::tc_fence_before();
     __syncthreads();

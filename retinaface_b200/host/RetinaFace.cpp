@@ -1,0 +1,63 @@
+// RetinaFace.cpp -- see RetinaFace.h.  Everything that computes lives behind the C ABI.
+#include "RetinaFace.h"
+
+#include <stdexcept>
+
+RetinaFace::RetinaFace(string &model, string network_, float nms, const RetinaFaceOptions &opt)
+    : opt_(opt), network(network_), nms_threshold(nms) {
+    // RetinaFace.cpp:211-271: only the fmc == 3 "net3" anchor configuration is ever set up
+    if (network != "net3") throw std::runtime_error("network setting error " + network + ": only net3 is configured");
+    const string path = model + "/" + opt_.model_file;
+    rf_config cfg{};
+    cfg.caffemodel_path = path.c_str();
+    cfg.precision = opt_.precision;
+    cfg.net_w = opt_.net_w;
+    cfg.net_h = opt_.net_h;
+    cfg.max_batch = opt_.max_batch;
+    cfg.max_faces = opt_.max_faces;
+    cfg.device = opt_.device;
+    cfg.max_image_w = opt_.max_image_w;
+    cfg.max_image_h = opt_.max_image_h;
+    int rc = rf_create(&cfg, &h_);
+    if (rc != RF_OK) throw std::runtime_error(string("rf_create: ") + rf_status_string(rc) + ": " + rf_last_error(nullptr));
+    rf_get_net_size(h_, nullptr, nullptr, nullptr, &opt_.max_faces);
+    out_faces_.resize((size_t)opt_.max_batch * opt_.max_faces);
+    out_counts_.resize(opt_.max_batch);
+}
+
+RetinaFace::~RetinaFace() { rf_destroy(h_); }
+
+void RetinaFace::detect(const Mat &img, float threshold, float /*scales*/) {
+    if (img.empty()) {   // RetinaFace.cpp:578-580
+        last_.clear();
+        return;
+    }
+    vector<cv::Mat> one(1, img);
+    detectBatchImages(one, threshold);
+}
+
+void RetinaFace::detectBatchImages(vector<cv::Mat> imgs, float threshold) {
+    last_.assign(imgs.size(), vector<FaceDetectInfo>());
+    scales_.assign(imgs.size(), 1.f);
+    const size_t mb = (size_t)opt_.max_batch;
+    for (size_t start = 0; start < imgs.size(); start += mb) {   // the reference asserts n <= maxBatchSize; chunk instead
+        const int n = (int)std::min(mb, imgs.size() - start);
+        vector<const uint8_t *> ptrs(n);
+        vector<int> ws(n), hs(n), strides(n);
+        for (int i = 0; i < n; i++) {
+            const cv::Mat &m = imgs[start + i];
+            if (m.empty()) throw std::runtime_error("detectBatchImages: empty image");
+            ptrs[i] = m.data; ws[i] = m.cols; hs[i] = m.rows; strides[i] = (int)m.step;
+            float sw = 1.0f * m.cols / opt_.net_w, sh = 1.0f * m.rows / opt_.net_h;   // RetinaFace.cpp:587-591
+            float sc = sw > sh ? sw : sh;
+            scales_[start + i] = sc > 1.0f ? sc : 1.0f;
+        }
+        int rc = rf_detect_batch(h_, ptrs.data(), ws.data(), hs.data(), strides.data(), n, threshold, nms_threshold,
+                                 out_faces_.data(), out_counts_.data(), nullptr);
+        if (rc != RF_OK) throw std::runtime_error(string("rf_detect_batch: ") + rf_status_string(rc) + ": " + rf_last_error(h_));
+        for (int i = 0; i < n; i++) {
+            const FaceDetectInfo *f = reinterpret_cast<const FaceDetectInfo *>(out_faces_.data() + (size_t)i * opt_.max_faces);
+            last_[start + i].assign(f, f + out_counts_[i]);
+        }
+    }
+}

@@ -1,0 +1,65 @@
+// main.cpp -- the reference's driver (retinaface/main.cpp:14-53) against the B200 class shell:
+// construct the detector from a model directory, then time detect() in a loop.  The reference
+// loops forever on a hard-coded JPEG; this one takes a raw BGR image (or synthesises noise) and
+// a finite iteration count so that it can run unattended.
+//   rf_main <model_dir> [--image raw.bgr W H] [--net W H] [--iters N] [--batch B] [--thr T]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "RetinaFace.h"
+
+int main(int argc, char **argv) {
+    if (argc < 2) {
+        std::fprintf(stderr, "usage: %s <model_dir> [--image raw.bgr W H] [--net W H] [--iters N] [--batch B] [--thr T]\n", argv[0]);
+        return 2;
+    }
+    string path = argv[1];
+    RetinaFaceOptions opt;
+    opt.net_w = 448; opt.net_h = 448;
+    int iters = 1000, batch = 1, iw = 448, ih = 448;
+    float thr = 0.9f;
+    string image;
+    for (int i = 2; i < argc; i++) {
+        if (!strcmp(argv[i], "--image") && i + 3 < argc) { image = argv[i + 1]; iw = atoi(argv[i + 2]); ih = atoi(argv[i + 3]); i += 3; }
+        else if (!strcmp(argv[i], "--net") && i + 2 < argc) { opt.net_w = atoi(argv[i + 1]); opt.net_h = atoi(argv[i + 2]); i += 2; }
+        else if (!strcmp(argv[i], "--iters") && i + 1 < argc) iters = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--batch") && i + 1 < argc) batch = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--thr") && i + 1 < argc) thr = (float)atof(argv[++i]);
+        else if (!strcmp(argv[i], "--model") && i + 1 < argc) opt.model_file = argv[++i];
+    }
+    opt.max_batch = batch > opt.max_batch ? batch : opt.max_batch;
+    try {
+        RetinaFace *rf = new RetinaFace(path, "net3", 0.4, opt);
+        cv::Mat img(ih, iw, CV_8UC3);
+        if (!image.empty()) {
+            std::ifstream f(image, std::ios::binary);
+            if (!f.read((char *)img.data, (std::streamsize)iw * ih * 3)) { std::fprintf(stderr, "cannot read %s\n", image.c_str()); return 2; }
+        } else {
+            unsigned s = 12345;
+            for (size_t i = 0; i < (size_t)iw * ih * 3; i++) { s = s * 1664525u + 1013904223u; img.data[i] = (unsigned char)(s >> 24); }
+        }
+        vector<cv::Mat> imgs(batch, img);
+        float time = 0;
+        int count = 0;
+        for (int it = 0; it < iters; it++) {
+            auto t0 = std::chrono::steady_clock::now();
+            if (batch == 1) rf->detect(img, thr); else rf->detectBatchImages(imgs, thr);
+            time += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            count++;
+            if (count % 1000 == 0) printf("face detection average time = %f.\n", time / count);
+        }
+        printf("face detection average time = %f ms over %d calls (batch %d); %zu faces in image 0\n", time / count, count, batch,
+               rf->lastFaces().size());
+        for (const FaceDetectInfo &f : rf->lastFaces())
+            printf("  score %.4f box [%.2f %.2f %.2f %.2f] scale %.3f\n", f.score, f.rect.x1, f.rect.y1, f.rect.x2, f.rect.y2, rf->lastScale());
+        delete rf;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

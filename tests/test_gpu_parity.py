@@ -252,8 +252,8 @@ def test_fp16_tensor_core_layers_vs_oracle(golden_image):
         names = ["mobilenet0_relu0_fwd", "mobilenet0_relu2_fwd", "mobilenet0_relu4_fwd", "mobilenet0_relu6_fwd",
                  "mobilenet0_relu8_fwd", "mobilenet0_relu10_fwd", "mobilenet0_relu12_fwd", "mobilenet0_relu22_fwd",
                  "mobilenet0_relu24_fwd", "mobilenet0_relu26_fwd", "rf_c3_lateral_relu", "rf_c3_det_context_conv1_relu",
-                 "rf_c3_det_concat_relu", "rf_c2_lateral_relu", "_plus0", "rf_c2_aggr_relu", "rf_c2_det_concat_relu",
-                 "rf_c1_red_conv_relu", "_plus1", "rf_c1_aggr_relu", "rf_c1_det_context_conv1_relu",
+                 "rf_c3_det_concat_relu", "rf_c2_lateral_relu", "rf_c2_aggr_relu", "rf_c2_det_concat_relu",
+                 "rf_c1_red_conv_relu", "rf_c1_aggr_relu", "rf_c1_det_context_conv1_relu",
                  "rf_c1_det_context_conv3_1_relu", "rf_c1_det_concat_relu"]
         x = np.concatenate([preprocess_bgr_u8(b) for b in batch])
         ref = MnetOracle(caffemodel("mnet25")).forward(x, want=names)
