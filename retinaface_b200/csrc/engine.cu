@@ -292,9 +292,45 @@ void build_plan(rf_handle h) {
     auto Wd = [h](size_t off) { return h->d_weights + off; };
     const double es = h->elem;
 
-    // ---- conv0 (prototxt:11-53) -----------------------------------------------------------
+    // ---- stem ------------------------------------------------------------------------------------
+    int first_pair = 1;
     int cur_h = H / 2, cur_w = W / 2, cur_c = 8;
-    int cur = B.tensor("mobilenet0_relu0_fwd", cur_h, cur_w, 8);
+    int cur = -1;
+    bool stem_done = false;
+    if constexpr (std::is_same<T, __half>::value) {
+        if (h->use_tc) {
+            // conv0 + dw1 + pw2 fused on CUDA cores (kernels_simt.cuh k_stem)
+            const FoldedConv &c0 = m.conv("mobilenet0_conv0_fwd"), &dw = m.conv("mobilenet0_conv1_fwd"), &pw = m.conv("mobilenet0_conv2_fwd");
+            std::vector<float> w0(27 * 8), wd(72), wp(128);
+            for (int o = 0; o < 8; o++)
+                for (int cb = 0; cb < 3; cb++)
+                    for (int t = 0; t < 9; t++) w0[(t * 3 + cb) * 8 + o] = c0.w[((size_t)o * 3 + (2 - cb)) * 9 + t];
+            for (int c = 0; c < 8; c++)
+                for (int t = 0; t < 9; t++) wd[t * 8 + c] = dw.w[(size_t)c * 9 + t];
+            for (int o = 0; o < 16; o++)
+                for (int c = 0; c < 8; c++) wp[c * 16 + o] = pw.w[(size_t)o * 8 + c];
+            size_t ow0 = B.add_weights(w0), ob0 = B.add_weights(c0.b), owd = B.add_weights(wd), obd = B.add_weights(dw.b),
+                   owp = B.add_weights(wp), obp = B.add_weights(pw.b);
+            cur = B.tensor("mobilenet0_relu2_fwd", cur_h, cur_w, 16);
+            int out = cur;
+            Step s;
+            s.name = "stem_conv0+dw1+pw2_u8_to_16ch";
+            s.out = {out};
+            s.flops_per_img = 2.0 * cur_h * cur_w * (8 * 27 + 8 * 9 + 8 * 16);
+            s.bytes_per_img = (double)H * W * 3 + (double)cur_h * cur_w * 16 * es;
+            s.launch = [=](int n, cudaStream_t st) {
+                StemWeights sw{Wd(ow0), Wd(ob0), Wd(owd), Wd(obd), Wd(owp), Wd(obp)};
+                const int tiles = ((H / 2 + 15) / 16) * ((W / 2 + 15) / 16);
+                launch_k(k_stem, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, T_(out), sw, n, H, W);
+            };
+            B.step(std::move(s));
+            cur_c = 16;
+            first_pair = 3;
+            stem_done = true;
+        }
+    }
+    if (!stem_done) {
+    cur = B.tensor("mobilenet0_relu0_fwd", cur_h, cur_w, 8);
     {
         const FoldedConv &c = m.conv("mobilenet0_conv0_fwd");
         std::vector<float> wk(27 * 8);
@@ -314,9 +350,10 @@ void build_plan(rf_handle h) {
         };
         B.step(std::move(s));
     }
+    }
     // ---- 13 x (depthwise 3x3, pointwise 1x1) (prototxt:55-1192) -----------------------------
     int c1 = -1, c2 = -1, c3 = -1;
-    for (int i = 1; i <= 26; i += 2) {
+    for (int i = first_pair; i <= 26; i += 2) {
         const FoldedConv &dw = m.conv("mobilenet0_conv" + std::to_string(i) + "_fwd");
         const FoldedConv &pw = m.conv("mobilenet0_conv" + std::to_string(i + 1) + "_fwd");
         const int C = dw.cout, S = dw.stride;
@@ -424,7 +461,7 @@ void build_plan(rf_handle h) {
                     a.R = (ks == 3 ? 128 + 2 * (iw + 3) : 128) | 1;
                     a.wimg = h->d_weights_h + oimg; a.bias = Wd(ob);
                     a.out = TcOut{T_(t0) + off0, ld0, n0, relu0, t1 >= 0 ? T_(t1) + off1 : nullptr, ld1, relu1};
-                    if (tup >= 0) { a.up = T_(tup); a.up_w = Wd(oup); }
+                    if (tup >= 0) { a.up = T_(tup); a.up_w = Wd(oup); a.Cmax = (((a.R / a.Wp + 2) / 2 + 3) * (iw / 2)) | 1; }
                     launch_tc_conv(a, st);
                 };
                 B.step(std::move(s));

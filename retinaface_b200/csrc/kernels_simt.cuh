@@ -268,3 +268,116 @@ __global__ void __launch_bounds__(256) k_upsample_add(const T *__restrict__ late
 }
 
 }  // namespace rf
+
+namespace rf {
+
+// ------------------------------------------------------------------------------------------
+// Stem: mobilenet0_conv0 (3x3 s2, 3->8) + BN + ReLU -> conv1 (depthwise 3x3) + BN + ReLU -> conv2
+// (pointwise 8->16) + BN + ReLU   (prototxt:11-141) in ONE kernel, u8 BGR image in, FP16 NHWC
+// [n][H/2][W/2][16] out.  With 3/8/16 channels these layers are pure bandwidth/latency work (a 128x16x16
+// tensor-core tile would be >90% padding), so they run on CUDA cores from shared memory:
+//   per CTA: a 16x16 tile of the H/2 x W/2 map; the 37x37x3 u8 input patch is staged once, conv0 is
+//   evaluated on the 18x18 halo ring into shared memory (zero outside the map = conv1's padding), then
+//   each thread finishes one output pixel (depthwise + pointwise) in registers.
+// Intermediate activations stay in FP32 (they never leave the SM), only the result is rounded to FP16.
+//   w0: [27][8] (row = (ky*3+kx)*3 + c_bgr), b0[8]; wd: [9][8], bd[8]; wp: [8][16] (k-major), bp[16].
+// ------------------------------------------------------------------------------------------
+struct StemWeights { const float *w0, *b0, *wd, *bd, *wp, *bp; };
+
+__global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ run, __half *__restrict__ out, StemWeights sw,
+                                              int n, int H, int W) {
+    __shared__ uint8_t s_in[37][112];            // input patch rows, 37 px * 3 B (+1 pad)
+    __shared__ __align__(16) float s_c0[18 * 18][8];
+    __shared__ __align__(16) float s_w0[27 * 8 + 8];
+    __shared__ __align__(16) float s_wd[9 * 8 + 8];
+    __shared__ __align__(16) float s_wp[8 * 16 + 16];
+    const int tid = threadIdx.x;
+    const int OH = H >> 1, OW = W >> 1;
+    const int tiles_x = (OW + 15) >> 4, tiles_y = (OH + 15) >> 4;
+    const int b = blockIdx.x / (tiles_x * tiles_y);
+    const int trem = blockIdx.x - b * tiles_x * tiles_y;
+    const int oy0 = (trem / tiles_x) << 4, ox0 = (trem % tiles_x) << 4;
+    pdl_trigger();
+    for (int i = tid; i < 27 * 8 + 8; i += 256) s_w0[i] = i < 216 ? sw.w0[i] : sw.b0[i - 216];
+    for (int i = tid; i < 9 * 8 + 8; i += 256) s_wd[i] = i < 72 ? sw.wd[i] : sw.bd[i - 72];
+    for (int i = tid; i < 8 * 16 + 16; i += 256) s_wp[i] = i < 128 ? sw.wp[i] : sw.bp[i - 128];
+    pdl_wait();
+    // ---- stage the u8 patch: input rows 2*oy0-3 .. 2*oy0+33, columns 2*ox0-3 .. 2*ox0+33 -------------------
+    const uint8_t *__restrict__ img = run->input + (size_t)b * H * W * 3;
+    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+    for (int i = tid; i < 37 * 111; i += 256) {
+        const int r = i / 111, cb = i - r * 111;
+        const int iy = iy0 + r, ix = ix0 + cb / 3;
+        uint8_t v = 0;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[((size_t)iy * W + ix) * 3 + cb % 3];
+        s_in[r][cb] = v;
+    }
+    __syncthreads();
+    // ---- conv0 on the 18x18 ring (conv0 coordinates oy0-1 .. oy0+16) ---------------------------------------
+    for (int p = tid; p < 18 * 18; p += 256) {
+        const int py = p / 18, px = p - py * 18;
+        const int cy = oy0 - 1 + py, cx = ox0 - 1 + px;
+        float acc[8];
+        if (cy < 0 || cy >= OH || cx < 0 || cx >= OW) {
+#pragma unroll
+            for (int o = 0; o < 8; o++) acc[o] = 0.f;            // zero padding seen by the depthwise conv
+        } else {
+#pragma unroll
+            for (int o = 0; o < 8; o++) acc[o] = s_w0[216 + o];
+            // input row of tap ky: 2*cy + ky - 1 -> patch row 2*py + ky ; column likewise
+#pragma unroll 1
+            for (int ky = 0; ky < 3; ky++) {
+                const uint8_t *row = &s_in[2 * py + ky][(2 * px) * 3];
+#pragma unroll
+                for (int j = 0; j < 9; j++) {                    // j = kx*3 + c_bgr: 9 consecutive bytes
+                    const float v = (float)row[j];
+                    const float4 wa = *reinterpret_cast<const float4 *>(&s_w0[(ky * 9 + j) * 8]);
+                    const float4 wb = *reinterpret_cast<const float4 *>(&s_w0[(ky * 9 + j) * 8 + 4]);
+                    acc[0] = fmaf(v, wa.x, acc[0]); acc[1] = fmaf(v, wa.y, acc[1]); acc[2] = fmaf(v, wa.z, acc[2]); acc[3] = fmaf(v, wa.w, acc[3]);
+                    acc[4] = fmaf(v, wb.x, acc[4]); acc[5] = fmaf(v, wb.y, acc[5]); acc[6] = fmaf(v, wb.z, acc[6]); acc[7] = fmaf(v, wb.w, acc[7]);
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < 8; o++) acc[o] = fmaxf(acc[o], 0.f);
+        }
+        *reinterpret_cast<float4 *>(&s_c0[p][0]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4 *>(&s_c0[p][4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+    // ---- depthwise 3x3 + pointwise 8->16 for this thread's pixel ------------------------------------------
+    const int ty = tid >> 4, tx = tid & 15;
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    if (oy >= OH || ox >= OW) return;
+    float d[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) d[c] = s_wd[72 + c];
+#pragma unroll 1
+    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+            const float *src = &s_c0[(ty + ky) * 18 + tx + kx][0];
+            const float4 a0 = *reinterpret_cast<const float4 *>(src), a1 = *reinterpret_cast<const float4 *>(src + 4);
+            const float *w = &s_wd[(ky * 3 + kx) * 8];
+            d[0] = fmaf(a0.x, w[0], d[0]); d[1] = fmaf(a0.y, w[1], d[1]); d[2] = fmaf(a0.z, w[2], d[2]); d[3] = fmaf(a0.w, w[3], d[3]);
+            d[4] = fmaf(a1.x, w[4], d[4]); d[5] = fmaf(a1.y, w[5], d[5]); d[6] = fmaf(a1.z, w[6], d[6]); d[7] = fmaf(a1.w, w[7], d[7]);
+        }
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) o[j] = s_wp[128 + j];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const float v = fmaxf(d[c], 0.f);
+#pragma unroll
+        for (int j = 0; j < 16; j++) o[j] = fmaf(v, s_wp[c * 16 + j], o[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) o[j] = fmaxf(o[j], 0.f);
+    Vec8<__half> v0, v1;
+    v0.from_float(o);
+    v1.from_float(o + 8);
+    __half *dst = out + (((size_t)b * OH + oy) * OW + ox) * 16;
+    v0.store(dst);
+    v1.store(dst + 8);
+}
+
+}  // namespace rf

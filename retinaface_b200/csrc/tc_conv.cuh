@@ -142,6 +142,7 @@ struct TcConvArgs {
     // Eltwise SUM of prototxt:1585 / :1980 never exists as a tensor.  up: [nimg][H/2][W/2][Cin], up_w: [Cin][16].
     const __half *up;
     const float *up_w;
+    int Cmax;               // UPADD: staged coarse positions per tile, upper bound (odd)
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, bool valid) {
@@ -184,7 +185,7 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, int N, const float *s
 }
 
 inline size_t tc_conv_smem_bytes(const TcConvArgs &a) {
-    return (size_t)(a.Cin / 8) * a.R * 16 + (size_t)a.taps * a.Cin * a.N * 2 + 128;
+    return (size_t)(a.Cin / 8) * a.R * 16 + (size_t)a.taps * a.Cin * a.N * 2 + (a.up ? (size_t)(a.Cin / 8) * a.Cmax * 16 : 0) + 128;
 }
 
 template <int NT, bool UPADD>
@@ -194,7 +195,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     __shared__ uint32_t s_tmem;
     __shared__ int s_off[TC_MAX_R];      // staged position -> element offset of its pixel in `in`, -1 = zero padding
     __shared__ float s_bias[256];
-    __shared__ float s_uw[UPADD ? 64 * 16 : 1];
+    __shared__ __align__(16) float s_uw[UPADD ? 64 * 16 : 4];
+    __shared__ int s_crow[2];            // UPADD: [lo, hi] global coarse rows (b*UH + i) the tile reads
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int pad = a.taps == 9 ? 1 : 0;
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     const long lo = m0 - (long)(a.Wp + 1) * pad;
 
     if (tid == 0) {
+        s_crow[0] = 0x7fffffff; s_crow[1] = -1;
         tc::mbar_init(&bar_b, 1);
         tc::mbar_init(&bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     if (warp == 1) tc::tmem_alloc<NT>(&s_tmem);
     pdl_trigger();
     if (tid < a.N) s_bias[tid] = a.bias[tid];
-    if (UPADD) for (int i = tid; i < a.Cin * 16; i += TC_THREADS) s_uw[i] = a.up_w[i];
+    if (UPADD) for (int i = tid; i < a.Cin * 16; i += TC_THREADS) s_uw[(i & 15) * 64 + (i >> 4)] = a.up_w[i];   // [tap][channel]: conflict-free float4 reads
     for (int pl = tid; pl < a.R; pl += TC_THREADS) {
         const long p = lo + pl;
         int off = -1;
@@ -225,58 +228,80 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
             const int b = (int)(p / (a.Hp * a.Wp));
             const int rem = (int)(p - (long)b * a.Hp * a.Wp);
             const int yy = rem / a.Wp, xx = rem - yy * a.Wp;
-            if (yy < a.H && xx >= pad && xx < a.W + pad) off = ((b * a.H + yy) * a.W + (xx - pad)) * a.Cin;
+            if (yy < a.H && xx >= pad && xx < a.W + pad) {
+                off = ((b * a.H + yy) * a.W + (xx - pad)) * a.Cin;
+                if (UPADD) {
+                    const int UH = a.H >> 1, ih = (yy + 1) >> 1;
+                    atomicMin(&s_crow[0], b * UH + max(ih - 1, 0));
+                    atomicMax(&s_crow[1], b * UH + min(ih, UH - 1));
+                }
+            }
         }
         s_off[pl] = off;
     }
     __syncthreads();
     pdl_wait();                          // everything above is independent of the previous kernel's output
     // ---- stage the range: item = (position, 8-channel group), 16 B each --------------------------------
-    if (!UPADD) {
-        for (int it = tid; it < a.R * G; it += TC_THREADS) {
-            const int g = it % G, pl = it / G;
-            const int off = s_off[pl];
-            cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (off >= 0 ? off + g * 8 : 0), off >= 0);
+    for (int it = tid; it < a.R * G; it += TC_THREADS) {
+        const int g = it % G, pl = it / G;
+        const int off = s_off[pl];
+        cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (off >= 0 ? off + g * 8 : 0), off >= 0);
+    }
+    if (UPADD) {
+        // FPN merge: staged := lateral + crop(deconv_k4s2p1(up)).  The coarse rows the tile needs are staged
+        // with cp.async as well (one more contiguous range: global coarse rows [crow_lo, crow_hi]), so all global
+        // traffic of the tile is in flight at once; the add then runs shared -> shared, in the same operation
+        // order as k_upsample_add (kernels_simt.cuh): the staged FP16 values equal the unfused Eltwise tensor.
+        const int UH = a.H >> 1, UW = a.W >> 1;
+        unsigned char *sC = sB + (size_t)a.taps * a.Cin * a.N * 2;
+        const uint32_t lbo_c = (uint32_t)a.Cmax * 16;
+        const int crow_lo = s_crow[0], crow_hi = s_crow[1];
+        if (crow_hi >= crow_lo) {
+            const int ncp = (crow_hi - crow_lo + 1) * UW;
+            if (ncp > a.Cmax) __trap();
+            for (int it = tid; it < ncp * G; it += TC_THREADS) {
+                const int g = it % G, cp = it / G;
+                cp_async16_zfill(sC + (size_t)g * lbo_c + (size_t)cp * 16, a.up + ((size_t)crow_lo * UW + cp) * a.Cin + g * 8, true);
+            }
         }
         cp_async_wait_all();
-    } else {
-        // lateral + bilinear-deconv(up): same operation order as k_upsample_add (kernels_simt.cuh), so the
-        // staged FP16 values equal the ones the unfused Eltwise tensor would hold.
-        const int UH = a.H >> 1, UW = a.W >> 1;
+        __syncthreads();
         for (int it = tid; it < a.R * G; it += TC_THREADS) {
             const int g = it % G, pl = it / G;
             const int off = s_off[pl];
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (off >= 0) {
-                const int pix = off / a.Cin, c0 = g * 8;
-                const int x = pix % a.W, y = (pix / a.W) % a.H, b = pix / (a.W * a.H);
-                Vec8<__half> lv;
-                lv.load(a.in + off + c0);
-                float acc[8];
-                lv.to_float(acc);
-                const int i_hi = (y + 1) >> 1, j_hi = (x + 1) >> 1;
+            if (off < 0) continue;
+            const int pix = off / a.Cin, c0 = g * 8;
+            const int x = pix % a.W, y = (pix / a.W) % a.H, b = pix / (a.W * a.H);
+            unsigned char *slot = sS + (size_t)g * lbo_s + (size_t)pl * 16;
+            Vec8<__half> lv;
+            lv.v = *reinterpret_cast<const uint4 *>(slot);
+            float acc[8];
+            lv.to_float(acc);
+            const int i_hi = (y + 1) >> 1, j_hi = (x + 1) >> 1;
 #pragma unroll
-                for (int di = 0; di < 2; di++) {
-                    const int i = i_hi - di, ky = y - 2 * i + 1;
-                    if (i < 0 || i >= UH || ky < 0 || ky > 3) continue;
+            for (int di = 0; di < 2; di++) {
+                const int i = i_hi - di, ky = y - 2 * i + 1;
+                if (i < 0 || i >= UH || ky < 0 || ky > 3) continue;
 #pragma unroll
-                    for (int dj = 0; dj < 2; dj++) {
-                        const int j = j_hi - dj, kx = x - 2 * j + 1;
-                        if (j < 0 || j >= UW || kx < 0 || kx > 3) continue;
-                        Vec8<__half> uv;
-                        uv.load(a.up + (((size_t)b * UH + i) * UW + j) * a.Cin + c0);
-                        float f[8];
-                        uv.to_float(f);
-#pragma unroll
-                        for (int c = 0; c < 8; c++) acc[c] = fmaf(f[c], s_uw[(c0 + c) * 16 + ky * 4 + kx], acc[c]);
-                    }
+                for (int dj = 0; dj < 2; dj++) {
+                    const int j = j_hi - dj, kx = x - 2 * j + 1;
+                    if (j < 0 || j >= UW || kx < 0 || kx > 3) continue;
+                    Vec8<__half> uv;
+                    uv.v = *reinterpret_cast<const uint4 *>(sC + (size_t)g * lbo_c + (size_t)((b * UH + i - crow_lo) * UW + j) * 16);
+                    float f[8];
+                    uv.to_float(f);
+                    const float4 w0 = *reinterpret_cast<const float4 *>(&s_uw[(ky * 4 + kx) * 64 + c0]);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(&s_uw[(ky * 4 + kx) * 64 + c0 + 4]);
+                    acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]); acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+                    acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]); acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
                 }
-                Vec8<__half> o;
-                o.from_float(acc);
-                v = o.v;
             }
-            *reinterpret_cast<uint4 *>(sS + (size_t)g * lbo_s + (size_t)pl * 16) = v;
+            Vec8<__half> o;
+            o.from_float(acc);
+            *reinterpret_cast<uint4 *>(slot) = o.v;
         }
+    } else {
+        cp_async_wait_all();
     }
     tc::fence_async_smem();
     tc::tc_fence_before();

@@ -249,7 +249,7 @@ def test_fp16_tensor_core_layers_vs_oracle(golden_image):
         simt.debug_keep_all()
         h_tc = tc.forward_heads(batch)
         h_simt = simt.forward_heads(batch)
-        names = ["mobilenet0_relu0_fwd", "mobilenet0_relu2_fwd", "mobilenet0_relu4_fwd", "mobilenet0_relu6_fwd",
+        names = ["mobilenet0_relu2_fwd", "mobilenet0_relu4_fwd", "mobilenet0_relu6_fwd",
                  "mobilenet0_relu8_fwd", "mobilenet0_relu10_fwd", "mobilenet0_relu12_fwd", "mobilenet0_relu22_fwd",
                  "mobilenet0_relu24_fwd", "mobilenet0_relu26_fwd", "rf_c3_lateral_relu", "rf_c3_det_context_conv1_relu",
                  "rf_c3_det_concat_relu", "rf_c2_lateral_relu", "rf_c2_aggr_relu", "rf_c2_det_concat_relu",
