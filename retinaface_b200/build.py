@@ -63,5 +63,17 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_host(force: bool = False) -> str:
+    """C++ host side: the RetinaFace class shell + the main.cpp-style driver, linked against librf_b200.so."""
+    host = os.path.join(HERE, "host")
+    exe = os.path.join(HERE, "rf_main")
+    srcs = [os.path.join(host, f) for f in ("RetinaFace.cpp", "main.cpp")]
+    deps = srcs + [os.path.join(host, f) for f in ("RetinaFace.h", "cv_compat.hpp")] + [LIB]
+    if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-I", host, "-I", os.path.join(os.path.dirname(HERE), "include")] + srcs +
+                              ["-o", exe, "-L", HERE, "-lrf_b200", "-Wl,-rpath,$ORIGIN"])
+    return exe
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))

@@ -286,7 +286,7 @@ struct StemWeights { const float *w0, *b0, *wd, *bd, *wp, *bp; };
 
 __global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ run, __half *__restrict__ out, StemWeights sw,
                                               int n, int H, int W) {
-    __shared__ uint8_t s_in[37][112];            // input patch rows, 37 px * 3 B (+1 pad)
+    __shared__ __align__(4) uint8_t s_in[37][116];   // input patch rows: `mis` alignment bytes + 37 px * 3 B, as 29 words
     __shared__ __align__(16) float s_c0[18 * 18][8];
     __shared__ __align__(16) float s_w0[27 * 8 + 8];
     __shared__ __align__(16) float s_wd[9 * 8 + 8];
@@ -303,14 +303,30 @@ __global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ 
     for (int i = tid; i < 8 * 16 + 16; i += 256) s_wp[i] = i < 128 ? sw.wp[i] : sw.bp[i - 128];
     pdl_wait();
     // ---- stage the u8 patch: input rows 2*oy0-3 .. 2*oy0+33, columns 2*ox0-3 .. 2*ox0+33 -------------------
+    // 32-bit loads: the patch row starts at row byte cb0 = 3*ix0; words are taken from the 4-byte aligned
+    // address below it (`mis` bytes of slack), so a row is 29 word loads instead of 111 byte loads.  W is a
+    // multiple of 32, so every image row has the same alignment.  Words that straddle the image border are
+    // assembled bytewise.
     const uint8_t *__restrict__ img = run->input + (size_t)b * H * W * 3;
-    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
-    for (int i = tid; i < 37 * 111; i += 256) {
-        const int r = i / 111, cb = i - r * 111;
-        const int iy = iy0 + r, ix = ix0 + cb / 3;
-        uint8_t v = 0;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[((size_t)iy * W + ix) * 3 + cb % 3];
-        s_in[r][cb] = v;
+    const int iy0 = 2 * oy0 - 3, cb0 = (2 * ox0 - 3) * 3;
+    const int al0 = cb0 & ~3, mis = cb0 - al0;           // floor to a multiple of 4 (two's complement: also for cb0 < 0)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
+    const int rowbytes = W * 3;
+    for (int i = tid; i < 37 * 29; i += 256) {
+        const int r = i / 29, w = i - r * 29;
+        const int iy = iy0 + r, gb = al0 + 4 * w;        // first row byte of this word
+        uint32_t v = 0;
+        if (iy >= 0 && iy < H) {
+            const uint8_t *rowp = img + (size_t)iy * rowbytes;
+            if (aligned && gb >= 0 && gb + 3 < rowbytes) {
+                v = *reinterpret_cast<const uint32_t *>(rowp + gb);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (gb + k >= 0 && gb + k < rowbytes) v |= (uint32_t)rowp[gb + k] << (8 * k);
+            }
+        }
+        *reinterpret_cast<uint32_t *>(&s_in[r][4 * w]) = v;
     }
     __syncthreads();
     // ---- conv0 on the 18x18 ring (conv0 coordinates oy0-1 .. oy0+16) ---------------------------------------
@@ -327,7 +343,7 @@ __global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ 
             // input row of tap ky: 2*cy + ky - 1 -> patch row 2*py + ky ; column likewise
 #pragma unroll 1
             for (int ky = 0; ky < 3; ky++) {
-                const uint8_t *row = &s_in[2 * py + ky][(2 * px) * 3];
+                const uint8_t *row = &s_in[2 * py + ky][mis + (2 * px) * 3];
 #pragma unroll
                 for (int j = 0; j < 9; j++) {                    // j = kx*3 + c_bgr: 9 consecutive bytes
                     const float v = (float)row[j];
@@ -357,9 +373,10 @@ __global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ 
         for (int kx = 0; kx < 3; kx++) {
             const float *src = &s_c0[(ty + ky) * 18 + tx + kx][0];
             const float4 a0 = *reinterpret_cast<const float4 *>(src), a1 = *reinterpret_cast<const float4 *>(src + 4);
-            const float *w = &s_wd[(ky * 3 + kx) * 8];
-            d[0] = fmaf(a0.x, w[0], d[0]); d[1] = fmaf(a0.y, w[1], d[1]); d[2] = fmaf(a0.z, w[2], d[2]); d[3] = fmaf(a0.w, w[3], d[3]);
-            d[4] = fmaf(a1.x, w[4], d[4]); d[5] = fmaf(a1.y, w[5], d[5]); d[6] = fmaf(a1.z, w[6], d[6]); d[7] = fmaf(a1.w, w[7], d[7]);
+            const float4 w0 = *reinterpret_cast<const float4 *>(&s_wd[(ky * 3 + kx) * 8]);
+            const float4 w1 = *reinterpret_cast<const float4 *>(&s_wd[(ky * 3 + kx) * 8 + 4]);
+            d[0] = fmaf(a0.x, w0.x, d[0]); d[1] = fmaf(a0.y, w0.y, d[1]); d[2] = fmaf(a0.z, w0.z, d[2]); d[3] = fmaf(a0.w, w0.w, d[3]);
+            d[4] = fmaf(a1.x, w1.x, d[4]); d[5] = fmaf(a1.y, w1.y, d[5]); d[6] = fmaf(a1.z, w1.z, d[6]); d[7] = fmaf(a1.w, w1.w, d[7]);
         }
     float o[16];
 #pragma unroll
@@ -368,7 +385,11 @@ __global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ 
     for (int c = 0; c < 8; c++) {
         const float v = fmaxf(d[c], 0.f);
 #pragma unroll
-        for (int j = 0; j < 16; j++) o[j] = fmaf(v, s_wp[c * 16 + j], o[j]);
+        for (int j4 = 0; j4 < 4; j4++) {
+            const float4 w = *reinterpret_cast<const float4 *>(&s_wp[c * 16 + j4 * 4]);
+            o[j4 * 4 + 0] = fmaf(v, w.x, o[j4 * 4 + 0]); o[j4 * 4 + 1] = fmaf(v, w.y, o[j4 * 4 + 1]);
+            o[j4 * 4 + 2] = fmaf(v, w.z, o[j4 * 4 + 2]); o[j4 * 4 + 3] = fmaf(v, w.w, o[j4 * 4 + 3]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 16; j++) o[j] = fmaxf(o[j], 0.f);

@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     __shared__ float s_bias[256];
     __shared__ __align__(16) float s_uw[UPADD ? 64 * 16 : 4];
     __shared__ int s_crow[2];            // UPADD: [lo, hi] global coarse rows (b*UH + i) the tile reads
+    __shared__ int s_yx[UPADD ? TC_MAX_R : 1];   // UPADD: staged position -> (global fine row b*H+y) << 12 | x
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int pad = a.taps == 9 ? 1 : 0;
@@ -204,7 +205,6 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     const uint32_t lbo_s = (uint32_t)a.R * 16;
     unsigned char *sS = smem;
     unsigned char *sB = smem + (size_t)G * lbo_s;
-    const long P = (long)a.nimg * a.Hp * a.Wp;
     const long m0 = (long)blockIdx.x * 128;
     const long lo = m0 - (long)(a.Wp + 1) * pad;
 
@@ -221,29 +221,38 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     pdl_trigger();
     if (tid < a.N) s_bias[tid] = a.bias[tid];
     if (UPADD) for (int i = tid; i < a.Cin * 16; i += TC_THREADS) s_uw[(i & 15) * 64 + (i >> 4)] = a.up_w[i];   // [tap][channel]: conflict-free float4 reads
-    for (int pl = tid; pl < a.R; pl += TC_THREADS) {
-        const long p = lo + pl;
-        int off = -1;
-        if (p >= 0 && p < P) {
-            const int b = (int)(p / (a.Hp * a.Wp));
-            const int rem = (int)(p - (long)b * a.Hp * a.Wp);
-            const int yy = rem / a.Wp, xx = rem - yy * a.Wp;
-            if (yy < a.H && xx >= pad && xx < a.W + pad) {
-                off = ((b * a.H + yy) * a.W + (xx - pad)) * a.Cin;
-                if (UPADD) {
-                    const int UH = a.H >> 1, ih = (yy + 1) >> 1;
-                    atomicMin(&s_crow[0], b * UH + max(ih - 1, 0));
-                    atomicMax(&s_crow[1], b * UH + min(ih, UH - 1));
+    // position table, one warp per padded row (no per-position divisions): p = prow * Wp + xx
+    {
+        const int lane = tid & 31;
+        const long prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;          // floor
+        const long prow1 = (lo + a.R - 1) / a.Wp;
+        for (long prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
+            const int b = prow >= 0 ? (int)(prow / a.Hp) : -1;
+            const int yy = prow >= 0 ? (int)(prow - (long)b * a.Hp) : 0;
+            const bool rowok = prow >= 0 && b < a.nimg && yy < a.H;
+            for (int xx = lane; xx < a.Wp; xx += 32) {
+                const long pl = prow * a.Wp + xx - lo;
+                if (pl < 0 || pl >= a.R) continue;
+                int off = -1;
+                if (rowok && xx >= pad && xx < a.W + pad) {
+                    off = ((b * a.H + yy) * a.W + (xx - pad)) * a.Cin;
+                    if (UPADD) {
+                        s_yx[pl] = ((b * a.H + yy) << 12) | (xx - pad);
+                        const int UH = a.H >> 1, ih = (yy + 1) >> 1;
+                        atomicMin(&s_crow[0], b * UH + max(ih - 1, 0));
+                        atomicMax(&s_crow[1], b * UH + min(ih, UH - 1));
+                    }
                 }
+                s_off[pl] = off;
             }
         }
-        s_off[pl] = off;
     }
     __syncthreads();
     pdl_wait();                          // everything above is independent of the previous kernel's output
     // ---- stage the range: item = (position, 8-channel group), 16 B each --------------------------------
+    const int lg = 31 - __clz(G);        // G is a power of two (Cin in {16, 64, 128, 256})
     for (int it = tid; it < a.R * G; it += TC_THREADS) {
-        const int g = it % G, pl = it / G;
+        const int g = it & (G - 1), pl = it >> lg;
         const int off = s_off[pl];
         cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (off >= 0 ? off + g * 8 : 0), off >= 0);
     }
@@ -260,18 +269,20 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
             const int ncp = (crow_hi - crow_lo + 1) * UW;
             if (ncp > a.Cmax) __trap();
             for (int it = tid; it < ncp * G; it += TC_THREADS) {
-                const int g = it % G, cp = it / G;
+                const int g = it & (G - 1), cp = it >> lg;
                 cp_async16_zfill(sC + (size_t)g * lbo_c + (size_t)cp * 16, a.up + ((size_t)crow_lo * UW + cp) * a.Cin + g * 8, true);
             }
         }
         cp_async_wait_all();
         __syncthreads();
         for (int it = tid; it < a.R * G; it += TC_THREADS) {
-            const int g = it % G, pl = it / G;
+            const int g = it & (G - 1), pl = it >> lg;
             const int off = s_off[pl];
             if (off < 0) continue;
-            const int pix = off / a.Cin, c0 = g * 8;
-            const int x = pix % a.W, y = (pix / a.W) % a.H, b = pix / (a.W * a.H);
+            const int c0 = g * 8;
+            const int yx = s_yx[pl];
+            const int x = yx & 0xfff, gy = yx >> 12;             // gy = b*H + y
+            const int b = gy / a.H, y = gy - b * a.H;            // one division (vs three): b changes at most once per tile
             unsigned char *slot = sS + (size_t)g * lbo_s + (size_t)pl * 16;
             Vec8<__half> lv;
             lv.v = *reinterpret_cast<const uint4 *>(slot);
@@ -395,7 +406,6 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
     const long lo = centre(m0) - a.Wp - 1;
     const int R = (int)(centre(mlast) + a.Wp + 1 - lo) + 1;
     if (R > a.Rmax) __trap();            // host-side geometry (engine.cu dw_geometry) must bound every tile
-    const long P = (long)a.nimg * a.Hp * a.Wp;
 
     if (tid == 0) {
         tc::mbar_init(&bar_b, 1);
@@ -418,16 +428,20 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
             wreg[t][4] = w1.x; wreg[t][5] = w1.y; wreg[t][6] = w1.z; wreg[t][7] = w1.w;
         }
     }
-    for (int pl = tid; pl < R; pl += TC_THREADS) {
-        const long p = lo + pl;
-        int off = -1;
-        if (p >= 0 && p < P) {
-            const int b = (int)(p / (a.Hp * a.Wp));
-            const int rem = (int)(p - (long)b * a.Hp * a.Wp);
-            const int yy = rem / a.Wp, xx = rem - yy * a.Wp;
-            if (yy < a.IH && xx >= 1 && xx <= a.IW) off = ((b * a.IH + yy) * a.IW + (xx - 1)) * a.C;
+    {
+        const int lane = tid & 31;
+        const long prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;          // floor
+        const long prow1 = (lo + R - 1) / a.Wp;
+        for (long prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
+            const int b = prow >= 0 ? (int)(prow / a.Hp) : -1;
+            const int yy = prow >= 0 ? (int)(prow - (long)b * a.Hp) : 0;
+            const bool rowok = prow >= 0 && b < a.nimg && yy < a.IH;
+            for (int xx = lane; xx < a.Wp; xx += 32) {
+                const long pl = prow * a.Wp + xx - lo;
+                if (pl < 0 || pl >= R) continue;
+                s_off[pl] = (rowok && xx >= 1 && xx <= a.IW) ? ((b * a.IH + yy) * a.IW + (xx - 1)) * a.C : -1;
+            }
         }
-        s_off[pl] = off;
     }
     if (tid < 128) {
         const long m = m0 + tid;
@@ -435,8 +449,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
     }
     __syncthreads();
     pdl_wait();
+    const int lg = 31 - __clz(G);        // C / 8 is a power of two
     for (int it = tid; it < R * G; it += TC_THREADS) {
-        const int g = it % G, pl = it / G;
+        const int g = it & (G - 1), pl = it >> lg;
         const int off = s_off[pl];
         cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (off >= 0 ? off + g * 8 : 0), off >= 0);
     }

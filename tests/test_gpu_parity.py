@@ -299,3 +299,16 @@ def test_detector_class_mirror(golden_image):
     assert rf.detect(np.zeros((0, 0, 3), np.uint8), 0.9) == []
     per = rf.detectBatchImages([golden_image, golden_image[:400, :600]], 0.9)
     assert len(per) == 2 and len(per[0]) == 5
+
+
+def test_cpp_driver_on_golden_photo(golden_image, tmp_path):
+    """The C++ class shell through the main.cpp-style driver: raw BGR photo in, 5 faces out (448x448, thr 0.9)."""
+    import subprocess
+    from retinaface_b200.build import build_host
+    exe = build_host()
+    raw = tmp_path / "img.bgr"
+    raw.write_bytes(np.ascontiguousarray(golden_image).tobytes())
+    r = subprocess.run([exe, os.path.join(GOLDEN, "weights"), "--image", str(raw), "1280", "886", "--net", "448", "448", "--iters", "3"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "5 faces in image 0" in r.stdout and "score 0.99" in r.stdout

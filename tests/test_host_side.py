@@ -71,3 +71,16 @@ def test_detector_mirror_rejects_unconfigured_networks(built_lib):
     from retinaface_b200 import RetinaFace
     with pytest.raises(ValueError):
         RetinaFace("tests/golden/weights", "net5")
+
+
+def test_cpp_driver_builds_and_fails_loudly_without_gpu(built_lib):
+    """retinaface_b200/host (RetinaFace class shell + main.cpp-style driver) compiles against the C ABI;
+    without a GPU it must exit non-zero with the library's error, not fall back to anything."""
+    import subprocess
+    import torch
+    from retinaface_b200.build import build_host
+    exe = build_host()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "weights"), "--iters", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "no CPU path" in r.stderr
