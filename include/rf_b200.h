@@ -111,6 +111,17 @@ int rf_detect_batch(rf_handle h, const uint8_t *const *bgr_images, const int *wi
                     const int *row_strides, int n, float score_threshold, float nms_threshold,
                     rf_face *out_faces, int *out_counts, int32_t *out_anchor_index);
 
+/* Pipelined end to end (throughput mode of the same path): rf_submit_batch queues H2D (on a copy
+ * stream) + forward + D2H for one batch of NETWORK-SIZED images and returns at once with a ticket;
+ * rf_collect_batch blocks until that batch's faces are in the caller's arrays.  Up to
+ * RF_PIPELINE_DEPTH batches may be in flight, so the H2D copy of batch i+1 overlaps the kernels of
+ * batch i (host ingest).  Tickets must be collected in submission order.  Source
+ * images may be pinned (copied in place) or pageable (staged through the library's pinned ring). */
+#define RF_PIPELINE_DEPTH 3
+int rf_submit_batch(rf_handle h, const uint8_t *const *bgr_images, int n, float score_threshold, float nms_threshold,
+                    int *ticket);
+int rf_collect_batch(rf_handle h, int ticket, rf_face *out_faces, int *out_counts, int32_t *out_anchor_index);
+
 /* Device-resident variant: `dev_bgr` holds n network-sized u8 BGR HWC images (contiguous) in
  * device memory; results stay on the device: *dev_dets -> [max_batch][max_faces] rf_det,
  * *dev_counts -> [max_batch] int32 (kept count, clamped to max_faces).  Asynchronous on the

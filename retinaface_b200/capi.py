@@ -17,7 +17,7 @@ FACE_FLOATS = 15
 # every symbol include/rf_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
     "rf_abi_version", "rf_build_info", "rf_status_string", "rf_create", "rf_destroy", "rf_last_error",
-    "rf_pinned_input", "rf_device_input", "rf_detect_batch", "rf_detect_batch_device", "rf_forward_heads",
+    "rf_pinned_input", "rf_device_input", "rf_detect_batch", "rf_submit_batch", "rf_collect_batch", "rf_detect_batch_device", "rf_forward_heads",
     "rf_postprocess", "rf_preprocess", "rf_get_net_size", "rf_num_anchors", "rf_stream", "rf_synchronize",
     "rf_launches_per_batch", "rf_profile_layers", "rf_debug_get_tensor", "rf_debug_keep_all", "rf_model_inspect",
 ]
@@ -71,6 +71,8 @@ def load_library() -> C.CDLL:
     lib.rf_get_net_size.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
     lib.rf_detect_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rf_submit_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_float, C.POINTER(C.c_int)]
+    lib.rf_collect_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.rf_detect_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.rf_forward_heads.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -193,6 +195,26 @@ class Engine:
         _, ptrs, ws, hs = self._pin_args
         self._check(self.lib.rf_detect_batch(self.h, ptrs, ws, hs, None, n, thr, nms_thr, faces.ctypes.data,
                                              counts.ctypes.data, None))
+
+    def submit(self, images: Sequence[np.ndarray], thr: float, nms_thr: float) -> int:
+        """Pipelined path: queue one batch of network-sized images (H2D on the copy stream + forward + D2H);
+        returns a ticket for collect().  Up to 3 batches in flight."""
+        n = len(images)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in images])
+        t = C.c_int()
+        self._check(self.lib.rf_submit_batch(self.h, ptrs, n, thr, nms_thr, C.byref(t)))
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = (n, images)      # keep the sources alive until collected
+        return t.value
+
+    def collect(self, ticket: int, faces: Optional[np.ndarray] = None, counts: Optional[np.ndarray] = None):
+        n, _ = self._inflight.pop(ticket)
+        if faces is None:
+            faces = np.empty((n, self.max_faces, FACE_FLOATS), dtype=np.float32)
+        if counts is None:
+            counts = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.rf_collect_batch(self.h, ticket, faces.ctypes.data, counts.ctypes.data, None))
+        return faces, counts
 
     def detect_device(self, n: int, thr: float, nms_thr: float, dev_ptr: Optional[int] = None):
         """Asynchronous device-resident detect.  Returns (dets_ptr, counts_ptr) device addresses."""

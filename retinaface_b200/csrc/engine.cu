@@ -108,6 +108,17 @@ struct rf_handle_s {
     rf_det *h_dets = nullptr;         // pinned [max_batch][max_faces]
     int *h_counts = nullptr;          // pinned [2*max_batch]: kept, candidates
     std::map<int, cudaGraphExec_t> graphs;
+    // pipelined end-to-end path (rf_submit_batch / rf_collect_batch)
+    struct Slot {
+        uint8_t *d_in = nullptr, *h_in = nullptr;     // device input, pinned staging for pageable sources
+        rf_det *h_dets = nullptr;                      // pinned results
+        int *h_counts = nullptr;
+        cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
+        int n = 0;
+        bool busy = false;
+    } slots[RF_PIPELINE_DEPTH];
+    cudaStream_t copy_stream = nullptr;
+    unsigned submit_seq = 0, collect_seq = 0;
     cudaStream_t lane_stream[3] = {nullptr, nullptr, nullptr};   // [0] unused (the caller's stream is lane 0)
     std::vector<cudaEvent_t> step_event;
     bool blobs_in_plan = false;       // head step writes blobs (forward_heads path)
@@ -735,6 +746,12 @@ void destroy(rf_handle h) {
     cudaFree(h->pb.flag_scratch); cudaFree(h->pb.out_dets); cudaFree(h->pb.out_counts); cudaFree(h->pb.out_total_kept);
     for (auto p : h->d_blobs) cudaFree(p);
     cudaFreeHost(h->h_input); cudaFreeHost(h->h_raw); cudaFreeHost(h->h_params); cudaFreeHost(h->h_dets); cudaFreeHost(h->h_counts);
+    for (auto &sl : h->slots) {
+        cudaFree(sl.d_in); cudaFreeHost(sl.h_in); cudaFreeHost(sl.h_dets); cudaFreeHost(sl.h_counts);
+        if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto e : h->step_event) if (e) cudaEventDestroy(e);
     for (int l = 1; l < 3; l++) if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1017,6 +1034,92 @@ int rf_detect_batch(rf_handle h, const uint8_t *const *imgs, const int *widths, 
         forward_graph(h, n);
         fetch_results(h, n, out_faces, out_counts, out_idx, nullptr);
     } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+static void ensure_slots(rf_handle h) {
+    if (h->copy_stream) return;
+    const size_t in_bytes = (size_t)h->cfg.max_batch * h->cfg.net_h * h->cfg.net_w * 3;
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto &sl : h->slots) {
+        CK(cudaMalloc(&sl.d_in, in_bytes));
+        CK(cudaHostAlloc(&sl.h_in, in_bytes, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&sl.h_dets, sizeof(rf_det) * (size_t)h->cfg.max_batch * h->cfg.max_faces, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&sl.h_counts, sizeof(int) * h->cfg.max_batch, cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    }
+}
+
+int rf_submit_batch(rf_handle h, const uint8_t *const *imgs, int n, float thr, float nms, int *ticket) {
+    int rc = check_n(h, n);
+    if (rc) return rc;
+    if (!imgs || !ticket || n == 0) return fail(h, RF_ERR_INVALID_ARG, "rf_submit_batch: NULL argument or empty batch");
+    const size_t img_bytes = (size_t)h->cfg.net_h * h->cfg.net_w * 3;
+    try {
+        CK(cudaSetDevice(h->device));
+        ensure_slots(h);
+        rf_handle_s::Slot &sl = h->slots[h->submit_seq % RF_PIPELINE_DEPTH];
+        if (sl.busy) return fail(h, RF_ERR_CAPACITY, "rf_submit_batch: RF_PIPELINE_DEPTH batches already in flight; collect one first");
+        // H2D on the copy stream: adjacent sources collapse into one copy
+        const uint8_t *run_src = nullptr;
+        int run_start = -1, run_len = 0;
+        auto flush = [&]() {
+            if (run_start < 0) return;
+            CK(cudaMemcpyAsync(sl.d_in + (size_t)run_start * img_bytes, run_src, (size_t)run_len * img_bytes, cudaMemcpyHostToDevice,
+                               h->copy_stream));
+            run_start = -1;
+        };
+        for (int i = 0; i < n; i++) {
+            if (!imgs[i]) return fail(h, RF_ERR_INVALID_ARG, fmt("rf_submit_batch: image %d is NULL", i));
+            const uint8_t *src = imgs[i];
+            cudaPointerAttributes at{};
+            bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+            if (!pinned) {
+                cudaGetLastError();
+                memcpy(sl.h_in + (size_t)i * img_bytes, src, img_bytes);   // slot is free: its previous H2D completed before collect
+                src = sl.h_in + (size_t)i * img_bytes;
+            }
+            if (run_start >= 0 && src == run_src + (size_t)run_len * img_bytes) run_len++;
+            else { flush(); run_start = i; run_src = src; run_len = 1; }
+        }
+        flush();
+        CK(cudaEventRecord(sl.ev_h2d, h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, sl.ev_h2d, 0));
+        if (h->param_seq && h->param_seq % rf_handle_s::kParamSlots == 0) CK(cudaStreamSynchronize(h->stream));
+        set_params(h, thr, nms, sl.d_in);
+        forward_graph(h, n);
+        CK(cudaMemcpyAsync(sl.h_counts, h->pb.out_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(sl.h_dets, h->pb.out_dets, sizeof(rf_det) * (size_t)n * h->cfg.max_faces, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(sl.ev_done, h->stream));
+        sl.n = n;
+        sl.busy = true;
+        *ticket = (int)h->submit_seq++;
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+int rf_collect_batch(rf_handle h, int ticket, rf_face *out_faces, int *out_counts, int32_t *out_idx) {
+    if (!h) return RF_ERR_INVALID_ARG;
+    if ((unsigned)ticket != h->collect_seq) return fail(h, RF_ERR_INVALID_ARG, fmt("rf_collect_batch: ticket %d out of order (next is %u)", ticket, h->collect_seq));
+    rf_handle_s::Slot &sl = h->slots[h->collect_seq % RF_PIPELINE_DEPTH];
+    if (!sl.busy) return fail(h, RF_ERR_INVALID_ARG, "rf_collect_batch: nothing submitted under this ticket");
+    try {
+        CK(cudaSetDevice(h->device));
+        CK(cudaEventSynchronize(sl.ev_done));
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    const int mf = h->cfg.max_faces;
+    for (int i = 0; i < sl.n; i++) {
+        const int k = sl.h_counts[i];
+        if (out_counts) out_counts[i] = k;
+        for (int j = 0; j < k; j++) {
+            const rf_det &d = sl.h_dets[(size_t)i * mf + j];
+            if (out_faces) out_faces[(size_t)i * mf + j] = d.face;
+            if (out_idx) out_idx[(size_t)i * mf + j] = d.anchor_index;
+        }
+    }
+    sl.busy = false;
+    h->collect_seq++;
     return RF_OK;
 }
 
