@@ -248,10 +248,10 @@ void launch_tc_dwpw(const TcDwArgs &a, int nsplit, cudaStream_t s) {
     dim3 grid((unsigned)((M + a.rows - 1) / a.rows), nsplit);
     const size_t smem = tc_dw_smem_bytes(a);
     switch (tc_tmem_cols(a.N)) {
-        case 32: launch_k(k_tc_dwpw_staged<32>, grid, dim3(TC_THREADS), smem, s, a); break;
-        case 64: launch_k(k_tc_dwpw_staged<64>, grid, dim3(TC_THREADS), smem, s, a); break;
-        case 128: launch_k(k_tc_dwpw_staged<128>, grid, dim3(TC_THREADS), smem, s, a); break;
-        default: launch_k(k_tc_dwpw_staged<256>, grid, dim3(TC_THREADS), smem, s, a); break;
+        case 32: if (a.C >= 64) launch_k(k_tc_dwpw_staged<32, true>, grid, dim3(TC_THREADS), smem, s, a); else launch_k(k_tc_dwpw_staged<32, false>, grid, dim3(TC_THREADS), smem, s, a); break;
+        case 64: if (a.C >= 64) launch_k(k_tc_dwpw_staged<64, true>, grid, dim3(TC_THREADS), smem, s, a); else launch_k(k_tc_dwpw_staged<64, false>, grid, dim3(TC_THREADS), smem, s, a); break;
+        case 128: if (a.C >= 64) launch_k(k_tc_dwpw_staged<128, true>, grid, dim3(TC_THREADS), smem, s, a); else launch_k(k_tc_dwpw_staged<128, false>, grid, dim3(TC_THREADS), smem, s, a); break;
+        default: if (a.C >= 64) launch_k(k_tc_dwpw_staged<256, true>, grid, dim3(TC_THREADS), smem, s, a); else launch_k(k_tc_dwpw_staged<256, false>, grid, dim3(TC_THREADS), smem, s, a); break;
     }
 }
 constexpr int TC_SMEM_LIMIT = 200 * 1024;   // dynamic; the kernels also hold ~20 KB static
@@ -260,7 +260,8 @@ cudaError_t tc_init() {
 #define RF_TC_ATTR(K_) if ((e = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT))) return e
     RF_TC_ATTR((k_tc_conv_staged<32, false>)); RF_TC_ATTR((k_tc_conv_staged<64, false>)); RF_TC_ATTR((k_tc_conv_staged<128, false>)); RF_TC_ATTR((k_tc_conv_staged<256, false>));
     RF_TC_ATTR((k_tc_conv_staged<32, true>)); RF_TC_ATTR((k_tc_conv_staged<64, true>)); RF_TC_ATTR((k_tc_conv_staged<128, true>)); RF_TC_ATTR((k_tc_conv_staged<256, true>));
-    RF_TC_ATTR(k_tc_dwpw_staged<32>); RF_TC_ATTR(k_tc_dwpw_staged<64>); RF_TC_ATTR(k_tc_dwpw_staged<128>); RF_TC_ATTR(k_tc_dwpw_staged<256>);
+    RF_TC_ATTR((k_tc_dwpw_staged<32, true>)); RF_TC_ATTR((k_tc_dwpw_staged<64, true>)); RF_TC_ATTR((k_tc_dwpw_staged<128, true>)); RF_TC_ATTR((k_tc_dwpw_staged<256, true>));
+    RF_TC_ATTR((k_tc_dwpw_staged<32, false>)); RF_TC_ATTR((k_tc_dwpw_staged<64, false>)); RF_TC_ATTR((k_tc_dwpw_staged<128, false>)); RF_TC_ATTR((k_tc_dwpw_staged<256, false>));
 #undef RF_TC_ATTR
     return cudaSuccess;
 }
@@ -566,8 +567,31 @@ void build_plan(rf_handle h) {
     }
     ssh("c2", aggr2, h16, w16, 1, lanes ? 2 : 0);
     int aggr1 = B.tensor("rf_c1_aggr_relu", h8, w8, 64);
-    if (h->use_tc) {
+    // Fusing the merge into the aggr conv costs ~50 KB of shared memory: fine while the conv's tiles fit one
+    // wave (c2 level), a loss once it forces a second wave (c1 level at batch 8: 207 tiles, 1 CTA/SM).
+    const long c1_tiles = ((long)h->cfg.max_batch * (h8 + 1) * (w8 + 2) + 127) / 128;
+    if (h->use_tc && c1_tiles <= 148) {
         conv_step("c1_upsample+add+aggr_3x3_64to64", {&m.conv("rf_c1_aggr")}, lat1, h8, w8, aggr1, 64, 0, 64, 1, -1, 0, 0, 0, 0, aggr2, 1);
+    } else if (h->use_tc) {
+        if constexpr (std::is_same<T, __half>::value) {
+            std::vector<__half> uwh(16 * 64);
+            for (int c = 0; c < 64; c++)
+                for (int t = 0; t < 16; t++) uwh[t * 64 + c] = __float2half(m.up_w[1][c * 16 + t]);
+            size_t ouw = B.add_weights_h(uwh);
+            int plus1 = B.tensor("_plus1", h8, w8, 64);
+            Step s;
+            s.name = "fpn_merge_c1_upsample+add_h2";
+            s.in = {lat1, aggr2}; s.out = {plus1};
+            s.flops_per_img = 2.0 * h8 * w8 * 64 * 4;
+            s.bytes_per_img = ((double)h8 * w8 * 64 * 2 + (double)(h8 / 2) * (w8 / 2) * 64) * es;
+            s.launch = [=](int n, cudaStream_t st) {
+                long total = (long)n * h8 * w8 * 8;
+                launch_k(k_fpn_merge_h2, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const __half *)T_(lat1), (const __half *)T_(aggr2),
+                         (__half *)T_(plus1), (const __half *)(h->d_weights_h + ouw), n, h8, w8, 64);
+            };
+            B.step(std::move(s));
+            conv_step("c1_aggr_3x3_64to64", {&m.conv("rf_c1_aggr")}, plus1, h8, w8, aggr1, 64, 0, 64, 1, -1, 0, 0, 0);
+        }
     } else {
         int plus1 = upadd("_plus1", lat1, aggr2, h8, w8, 1);
         conv_step("c1_aggr_3x3_64to64", {&m.conv("rf_c1_aggr")}, plus1, h8, w8, aggr1, 64, 0, 64, 1, -1, 0, 0, 0);

@@ -402,3 +402,55 @@ __global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ 
 }
 
 }  // namespace rf
+
+namespace rf {
+
+// ------------------------------------------------------------------------------------------
+// FPN merge, FP16 fast path: out = lateral + crop(deconv_k4s2p1_depthwise(up)) (prototxt:1948-1987) with packed
+// HFMA2 arithmetic (the deconvolution weights 1/16, 3/16, 9/16 are exact in FP16; the sum is stored as FP16
+// anyway).  One thread per (pixel, 8 channels); the lateral vector and the (up to) four coarse vectors are
+// loaded up front so all five global loads of a thread are in flight together.  Used where fusing the merge
+// into the consumer's staging (tc_conv.cuh UPADD) would push that kernel beyond one wave of CTAs.
+//   uwh: [16 taps][C] FP16 weights.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fpn_merge_h2(const __half *__restrict__ lateral, const __half *__restrict__ up,
+                                                      __half *__restrict__ out, const __half *__restrict__ uwh, int n, int H, int W, int C) {
+    pdl_trigger();
+    const int cg = C >> 3, UH = H >> 1, UW = W >> 1;
+    const long total = (long)n * H * W * cg;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % cg);
+    const long pix = idx / cg;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+    const int c0 = g * 8;
+    const int i_hi = (y + 1) >> 1, j_hi = (x + 1) >> 1;
+    int ci[2], cj[2], ky[2], kx[2];
+    bool vi[2], vj[2];
+#pragma unroll
+    for (int d = 0; d < 2; d++) {
+        ci[d] = i_hi - d; ky[d] = y - 2 * ci[d] + 1; vi[d] = ci[d] >= 0 && ci[d] < UH;
+        cj[d] = j_hi - d; kx[d] = x - 2 * cj[d] + 1; vj[d] = cj[d] >= 0 && cj[d] < UW;
+    }
+    uint4 wv[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) wv[t] = __ldg(reinterpret_cast<const uint4 *>(uwh + (ky[t >> 1] * 4 + kx[t & 1]) * C + c0));   // weights: not produced by the previous kernel
+    pdl_wait();
+    uint4 accv = *reinterpret_cast<const uint4 *>(lateral + (size_t)pix * C + c0);
+    uint4 uv[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const bool ok = vi[t >> 1] && vj[t & 1];
+        uv[t] = ok ? *reinterpret_cast<const uint4 *>(up + (((size_t)b * UH + ci[t >> 1]) * UW + cj[t & 1]) * C + c0) : make_uint4(0, 0, 0, 0);
+    }
+    __half2 *acc = reinterpret_cast<__half2 *>(&accv);
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const __half2 *u2 = reinterpret_cast<const __half2 *>(&uv[t]), *w2 = reinterpret_cast<const __half2 *>(&wv[t]);
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[c] = __hfma2(u2[c], w2[c], acc[c]);
+    }
+    *reinterpret_cast<uint4 *>(out + (size_t)pix * C + c0) = accv;
+}
+
+}  // namespace rf

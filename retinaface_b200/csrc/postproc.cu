@@ -23,7 +23,8 @@ namespace rf {
 namespace {
 
 constexpr int NMS_THREADS = 512;
-constexpr int NMS_SMEM_CAP = 4096;  // candidates sorted / suppressed entirely in shared memory
+constexpr int NMS_SMEM_CAP = 1024;  // candidates sorted / suppressed entirely in (static) shared memory
+constexpr int NMS_RANK_MAX = 256;   // up to here a one-pass rank sort replaces the bitonic ladder
 
 __device__ __forceinline__ unsigned long long make_key(float score, int emit) {
     unsigned u = __float_as_uint(score);
@@ -209,11 +210,18 @@ __device__ __forceinline__ bool suppresses(const float4 s, float area1, const fl
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area1, area2), inter)) > thr;
 }
 
-// One CTA per image.  (1) bitonic sort of the candidate keys, (2) greedy suppression rounds: the
-// next unsuppressed candidate is kept, then all threads test the remaining ones against it --
-// the same O(n * kept) work as the reference, parallel inside a round, (3) gather kept records.
+// One CTA per image.  (1) sort the candidate keys (rank sort for <= 256 candidates -- one pass, no
+// log^2 barrier ladder; bitonic above), (2) greedy suppression rounds: the next unsuppressed candidate is
+// kept, then all threads test the remaining ones against it -- the same O(n * kept) work as the reference,
+// parallel inside a round, (3) gather kept records.  Up to NMS_SMEM_CAP candidates live entirely in static
+// shared memory; beyond that (stress inputs) keys / flags use the global scratch of PostBuffers.
 __global__ void __launch_bounds__(NMS_THREADS) k_nms(const PostParams *__restrict__ params, PostBuffers pb) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ int s_kept[];                         // [max_faces]
+    __shared__ unsigned long long s_keys[NMS_SMEM_CAP];
+    __shared__ unsigned long long s_tmp[NMS_RANK_MAX];
+    __shared__ float4 s_box[NMS_SMEM_CAP];
+    __shared__ unsigned char s_flag[NMS_SMEM_CAP];
+    __shared__ int s_nkept;
     const int img = blockIdx.x;
     const int tid = threadIdx.x;
     const int A = pb.anchors_per_image;
@@ -224,34 +232,41 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms(const PostParams *__restric
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     const bool small = np2 <= NMS_SMEM_CAP;
-    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem);
-    float4 *s_box = reinterpret_cast<float4 *>(smem + sizeof(unsigned long long) * NMS_SMEM_CAP);
-    unsigned char *s_flag = smem + (sizeof(unsigned long long) + sizeof(float4)) * NMS_SMEM_CAP;
-    int *s_kept = reinterpret_cast<int *>(s_flag + NMS_SMEM_CAP);
-    __shared__ int s_nkept;
-
     unsigned long long *keys = small ? s_keys : pb.sort_scratch + (size_t)img * pb.anchors_pow2;
     unsigned char *flag = small ? s_flag : pb.flag_scratch + (size_t)img * pb.anchors_pow2;
     const unsigned long long *gkeys = pb.cand_keys + (size_t)img * A;
     const rf_det *recs = pb.cand_recs + (size_t)img * A;
-
-    for (int i = tid; i < np2; i += NMS_THREADS) {
-        keys[i] = i < n ? gkeys[i] : ~0ull;
-        flag[i] = 0;
-    }
     if (tid == 0) s_nkept = 0;
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < np2; i += NMS_THREADS) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long a = keys[i], b = keys[ixj];
-                    bool up = (i & k) == 0;
-                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+
+    if (n <= NMS_RANK_MAX) {
+        // rank sort: keys are unique (the emission index is part of the key), so rank = #smaller keys
+        for (int i = tid; i < n; i += NMS_THREADS) { s_tmp[i] = gkeys[i]; s_flag[i] = 0; }
+        __syncthreads();
+        for (int i = tid; i < n; i += NMS_THREADS) {
+            const unsigned long long k = s_tmp[i];
+            int rank = 0;
+            for (int j = 0; j < n; j++) rank += s_tmp[j] < k;
+            s_keys[rank] = k;
+        }
+        __syncthreads();
+    } else {
+        for (int i = tid; i < np2; i += NMS_THREADS) {
+            keys[i] = i < n ? gkeys[i] : ~0ull;
+            flag[i] = 0;
+        }
+        __syncthreads();
+        for (int k = 2; k <= np2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < np2; i += NMS_THREADS) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        unsigned long long a = keys[i], b = keys[ixj];
+                        bool up = (i & k) == 0;
+                        if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
     if (small) {
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms(const PostParams *__restric
     };
     int nkept = 0;  // thread 0's running count (mirrored to s_nkept at the end)
     for (int i = 0; i < n; i++) {
-        if (flag[i]) continue;  // uniform: flags of position i are final (see header comment)
+        if (flag[i]) continue;  // uniform: flags of position i are final once every earlier kept round has synchronised
         const float4 s = box_at(i);
         if (tid == 0) {
             if (nkept < pb.max_faces) s_kept[nkept] = i;
@@ -300,9 +315,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms(const PostParams *__restric
     }
 }
 
-size_t nms_smem_bytes(int max_faces) {
-    return (sizeof(unsigned long long) + sizeof(float4) + 1) * (size_t)NMS_SMEM_CAP + sizeof(int) * (size_t)max_faces;
-}
+size_t nms_smem_bytes(int max_faces) { return sizeof(int) * (size_t)max_faces; }
 
 }  // namespace
 
@@ -345,7 +358,7 @@ void launch_nms(int n, const PostParams *params, const PostBuffers &pb, cudaStre
 }
 
 cudaError_t postproc_init() {
-    // worst case max_faces is bounded by the engine (<= 8192): reserve for that
+    // static 27 KB + up to 32 KB dynamic (max_faces <= 8192) exceeds the 48 KB default: opt in once
     return cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes(8192));
 }
 

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     __shared__ uint32_t s_tmem;
     __shared__ int s_off[TC_MAX_R];      // staged position -> element offset of its pixel in `in`, -1 = zero padding
     __shared__ float s_bias[256];
-    __shared__ __align__(16) float s_uw[UPADD ? 64 * 16 : 4];
+    __shared__ __align__(16) __half s_uw[UPADD ? 64 * 16 : 8];   // [tap][channel] deconv weights as FP16 (bilinear taps are exact)
     __shared__ int s_crow[2];            // UPADD: [lo, hi] global coarse rows (b*UH + i) the tile reads
     __shared__ int s_yx[UPADD ? TC_MAX_R : 1];   // UPADD: staged position -> (global fine row b*H+y) << 12 | x
 
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     if (warp == 1) tc::tmem_alloc<NT>(&s_tmem);
     pdl_trigger();
     if (tid < a.N) s_bias[tid] = a.bias[tid];
-    if (UPADD) for (int i = tid; i < a.Cin * 16; i += TC_THREADS) s_uw[(i & 15) * 64 + (i >> 4)] = a.up_w[i];   // [tap][channel]: conflict-free float4 reads
+    if (UPADD) for (int i = tid; i < a.Cin * 16; i += TC_THREADS) s_uw[(i & 15) * 64 + (i >> 4)] = __float2half_rn(a.up_w[i]);
     // position table, one warp per padded row (no per-position divisions): p = prow * Wp + xx
     {
         const int lane = tid & 31;
@@ -284,10 +284,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
             const int x = yx & 0xfff, gy = yx >> 12;             // gy = b*H + y
             const int b = gy / a.H, y = gy - b * a.H;            // one division (vs three): b changes at most once per tile
             unsigned char *slot = sS + (size_t)g * lbo_s + (size_t)pl * 16;
-            Vec8<__half> lv;
-            lv.v = *reinterpret_cast<const uint4 *>(slot);
-            float acc[8];
-            lv.to_float(acc);
+            // packed FP16 arithmetic (HFMA2): the sum of <= 5 terms is stored as FP16 anyway; the reference's
+            // deconvolution weights (1/16, 3/16, 9/16) are exact in FP16
+            uint4 accv = *reinterpret_cast<const uint4 *>(slot);
+            __half2 *acc = reinterpret_cast<__half2 *>(&accv);
             const int i_hi = (y + 1) >> 1, j_hi = (x + 1) >> 1;
 #pragma unroll
             for (int di = 0; di < 2; di++) {
@@ -297,19 +297,14 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
                 for (int dj = 0; dj < 2; dj++) {
                     const int j = j_hi - dj, kx = x - 2 * j + 1;
                     if (j < 0 || j >= UW || kx < 0 || kx > 3) continue;
-                    Vec8<__half> uv;
-                    uv.v = *reinterpret_cast<const uint4 *>(sC + (size_t)g * lbo_c + (size_t)((b * UH + i - crow_lo) * UW + j) * 16);
-                    float f[8];
-                    uv.to_float(f);
-                    const float4 w0 = *reinterpret_cast<const float4 *>(&s_uw[(ky * 4 + kx) * 64 + c0]);
-                    const float4 w1 = *reinterpret_cast<const float4 *>(&s_uw[(ky * 4 + kx) * 64 + c0 + 4]);
-                    acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]); acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
-                    acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]); acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+                    const uint4 uv = *reinterpret_cast<const uint4 *>(sC + (size_t)g * lbo_c + (size_t)((b * UH + i - crow_lo) * UW + j) * 16);
+                    const uint4 wv = *reinterpret_cast<const uint4 *>(&s_uw[(ky * 4 + kx) * 64 + c0]);
+                    const __half2 *u2 = reinterpret_cast<const __half2 *>(&uv), *w2 = reinterpret_cast<const __half2 *>(&wv);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[c] = __hfma2(u2[c], w2[c], acc[c]);
                 }
             }
-            Vec8<__half> o;
-            o.from_float(acc);
-            *reinterpret_cast<uint4 *>(slot) = o.v;
+            *reinterpret_cast<uint4 *>(slot) = accv;
         }
     } else {
         cp_async_wait_all();
@@ -379,14 +374,18 @@ inline size_t tc_dw_smem_bytes(const TcDwArgs &a) {
     return (size_t)((a.C + 7) / 8) * a.Rmax * 16 + (size_t)(a.Kpad / 8) * TC_LBO_A + (size_t)a.Kpad * a.N * 2 + 128;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a) {
+// WREG: depthwise weights in registers (C >= 64: few threads share a channel group) or in shared memory
+// (small C, thousands of CTAs: registers are better spent on occupancy; all lanes of a warp read the same
+// few addresses, so the shared reads are broadcasts).
+template <int NT, bool WREG>
+__global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 3) k_tc_dwpw_staged(const TcDwArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_b, bar_done;
     __shared__ uint32_t s_tmem;
     __shared__ int s_off[TC_MAX_R];
     __shared__ int s_cpos[128];          // GEMM row -> staged index of its stencil centre, -1 = no output
     __shared__ float s_bias[256];
+    __shared__ __align__(16) float s_dw[WREG ? 4 : 10 * 64];   // !WREG: [tap][C] weights, [9] = bias (C <= 64)
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int G = a.C >> 3;
@@ -418,10 +417,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
     if (warp == 1) tc::tmem_alloc<NT>(&s_tmem);
     pdl_trigger();
     if (tid < a.N) s_bias[tid] = a.bias[blockIdx.y * a.N + tid];
-    float wreg[10][8];                   // [tap][channel] folded depthwise weights, [9] = bias
-    if (g_own < G) {
+    float wreg[WREG ? 10 : 1][8];        // [tap][channel] folded depthwise weights, [9] = bias
+    if (!WREG) {
+        for (int i = tid; i < 10 * a.C; i += TC_THREADS) s_dw[i] = i < 9 * a.C ? a.dw_w[i] : a.dw_b[i - 9 * a.C];
+    } else if (g_own < G) {
 #pragma unroll
-        for (int t = 0; t < 10; t++) {
+        for (int t = 0; t < (WREG ? 10 : 1); t++) {
             const float *src = (t < 9 ? a.dw_w + t * a.C : a.dw_b) + g_own * 8;
             const float4 w0 = __ldg(reinterpret_cast<const float4 *>(src)), w1 = __ldg(reinterpret_cast<const float4 *>(src) + 1);
             wreg[t][0] = w0.x; wreg[t][1] = w0.y; wreg[t][2] = w0.z; wreg[t][3] = w0.w;
@@ -465,8 +466,13 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
             const int cp = s_cpos[r];
             if (cp < 0) continue;            // rows beyond M (last tile): never read back
             float acc[8];
+            if (WREG) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] = wreg[9][i];
+                for (int i = 0; i < 8; i++) acc[i] = wreg[WREG ? 9 : 0][i];
+            } else {
+                const float4 b0 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g_own * 8]), b1 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g_own * 8 + 4]);
+                acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+            }
             const unsigned char *base = sS + (size_t)g_own * lbo_s + (size_t)cp * 16;
 #pragma unroll
             for (int t = 0; t < 9; t++) {
@@ -475,8 +481,14 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_dwpw_staged(const TcDwArgs a)
                 x.v = *reinterpret_cast<const uint4 *>(base + shift * 16);
                 float f[8];
                 x.to_float(f);
+                if (WREG) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] = fmaf(f[i], wreg[t][i], acc[i]);
+                    for (int i = 0; i < 8; i++) acc[i] = fmaf(f[i], wreg[WREG ? t : 0][i], acc[i]);
+                } else {
+                    const float4 w0 = *reinterpret_cast<const float4 *>(&s_dw[t * a.C + g_own * 8]), w1 = *reinterpret_cast<const float4 *>(&s_dw[t * a.C + g_own * 8 + 4]);
+                    acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]); acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+                    acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]); acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+                }
             }
 #pragma unroll
             for (int i = 0; i < 8; i++) acc[i] = fmaxf(acc[i], 0.f);
