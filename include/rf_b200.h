@@ -73,6 +73,9 @@ typedef struct rf_config {
     int device;                    /* CUDA device ordinal */
     int max_image_w, max_image_h;  /* largest caller image (reference: 4096x3072, RetinaFace.cpp:325); 0 -> net size */
     unsigned flags;                /* RF_FLAG_* */
+    int streams;                   /* execution contexts the asynchronous entry points rotate through so that
+                                      consecutive batches overlap on the GPU; 0 -> 2, max 4.  The blocking
+                                      rf_detect_batch always uses context 0. */
 } rf_config;
 
 #define RF_FLAG_NO_GRAPH      0x1u  /* launch kernels directly instead of replaying a CUDA graph */
@@ -150,7 +153,12 @@ int rf_preprocess(rf_handle h, const uint8_t *bgr, int width, int height, int ro
 int rf_get_net_size(rf_handle h, int *net_w, int *net_h, int *max_batch, int *max_faces);
 int rf_num_anchors(rf_handle h);            /* per image: 8,232 @448x448, 47,040 @1280x896 */
 void *rf_stream(rf_handle h);               /* cudaStream_t */
-int rf_synchronize(rf_handle h);
+int rf_synchronize(rf_handle h);            /* all execution contexts */
+/* rf_stream() is context 0's stream.  rf_fence() orders it after everything queued so far on every context
+ * (for CUDA-event timing of a run of rf_detect_batch_device calls); rf_last_stream() is the stream the last
+ * rf_detect_batch_device call was issued on (to order a collective on that call's device outputs). */
+int rf_fence(rf_handle h);
+void *rf_last_stream(rf_handle h);
 /* Number of kernel launches (graph kernel nodes) one rf_detect_batch_device of batch n issues. */
 int rf_launches_per_batch(rf_handle h, int n);
 /* Names + device times (ms, CUDA events, direct launches) of each kernel of one forward of

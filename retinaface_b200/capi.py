@@ -18,7 +18,7 @@ FACE_FLOATS = 15
 EXPORTS = [
     "rf_abi_version", "rf_build_info", "rf_status_string", "rf_create", "rf_destroy", "rf_last_error",
     "rf_pinned_input", "rf_device_input", "rf_detect_batch", "rf_submit_batch", "rf_collect_batch", "rf_detect_batch_device", "rf_forward_heads",
-    "rf_postprocess", "rf_preprocess", "rf_get_net_size", "rf_num_anchors", "rf_stream", "rf_synchronize",
+    "rf_postprocess", "rf_preprocess", "rf_get_net_size", "rf_num_anchors", "rf_stream", "rf_synchronize", "rf_fence", "rf_last_stream",
     "rf_launches_per_batch", "rf_profile_layers", "rf_debug_get_tensor", "rf_debug_keep_all", "rf_model_inspect",
 ]
 
@@ -32,7 +32,8 @@ class RfError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("caffemodel_path", C.c_char_p), ("int8_table_path", C.c_char_p), ("precision", C.c_int),
                 ("net_w", C.c_int), ("net_h", C.c_int), ("max_batch", C.c_int), ("max_faces", C.c_int),
-                ("device", C.c_int), ("max_image_w", C.c_int), ("max_image_h", C.c_int), ("flags", C.c_uint)]
+                ("device", C.c_int), ("max_image_w", C.c_int), ("max_image_h", C.c_int), ("flags", C.c_uint),
+                ("streams", C.c_int)]
 
 
 def lib_path() -> str:
@@ -65,7 +66,9 @@ def load_library() -> C.CDLL:
     lib.rf_device_input.argtypes = [C.c_void_p]
     lib.rf_stream.restype = C.c_void_p
     lib.rf_stream.argtypes = [C.c_void_p]
-    for name in ("rf_synchronize", "rf_num_anchors"):
+    lib.rf_last_stream.restype = C.c_void_p
+    lib.rf_last_stream.argtypes = [C.c_void_p]
+    for name in ("rf_synchronize", "rf_num_anchors", "rf_fence"):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.rf_launches_per_batch.argtypes = [C.c_void_p, C.c_int]
     lib.rf_get_net_size.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
@@ -115,10 +118,10 @@ class Engine:
 
     def __init__(self, caffemodel: str, net_h: int, net_w: int, precision: int = RF_PREC_FP16, max_batch: int = 8,
                  max_faces: int = 256, device: int = 0, int8_table: Optional[str] = None,
-                 max_image: Optional[Tuple[int, int]] = None, flags: int = 0):
+                 max_image: Optional[Tuple[int, int]] = None, flags: int = 0, streams: int = 0):
         self.lib = load_library()
         cfg = _Config(caffemodel.encode(), int8_table.encode() if int8_table else None, precision, net_w, net_h,
-                      max_batch, max_faces, device, max_image[1] if max_image else 0, max_image[0] if max_image else 0, flags)
+                      max_batch, max_faces, device, max_image[1] if max_image else 0, max_image[0] if max_image else 0, flags, streams)
         h = C.c_void_p()
         rc = self.lib.rf_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -163,6 +166,13 @@ class Engine:
 
     def synchronize(self):
         self._check(self.lib.rf_synchronize(self.h))
+
+    def fence(self):
+        """Order stream_ptr() after everything queued so far on every execution context."""
+        self._check(self.lib.rf_fence(self.h))
+
+    def last_stream_ptr(self) -> int:
+        return int(self.lib.rf_last_stream(self.h) or 0)
 
     # -- end to end ------------------------------------------------------------------------
     def detect_batch(self, images: Sequence[np.ndarray], thr: float, nms_thr: float, want_index: bool = False):

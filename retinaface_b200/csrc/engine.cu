@@ -127,7 +127,52 @@ struct rf_handle_s {
     float cur_thr = 0.5f, cur_nms = 0.4f;
 
     void *tptr(int id) const { return arena + tensors[id].offset; }
+
+    // Execution contexts.  Everything a forward pass writes (activation arena, candidate / output buffers,
+    // run parameters) and everything it is issued on (stream, lane streams, events, captured graphs) exists
+    // once per context; the asynchronous entry points rotate through the contexts so that consecutive batches
+    // overlap on the GPU (most kernels of one batch-8 step fill well under one wave of the 148 SMs).  The
+    // members above always hold the ACTIVE context; switch_ctx() swaps them with a saved one.
+    struct Ctx {
+        cudaStream_t stream = nullptr, lane_stream[3] = {nullptr, nullptr, nullptr};
+        std::vector<cudaEvent_t> step_event;
+        unsigned char *arena = nullptr;
+        PostBuffers pb{};
+        PostParams *d_params = nullptr, *h_params = nullptr;
+        unsigned param_seq = 0;
+        float cur_thr = 0.5f, cur_nms = 0.4f;
+        std::map<int, cudaGraphExec_t> graphs;
+        cudaEvent_t fence = nullptr;
+    };
+    std::vector<Ctx> saved;
+    int active = 0, nctx = 1;
+    unsigned next_dev_ctx = 0;
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t fence = nullptr;
 };
+
+namespace {
+void switch_ctx(rf_handle h, int i) {
+    if (i == h->active) return;
+    auto xchg = [&](rf_handle_s::Ctx &c) {
+        std::swap(c.stream, h->stream);
+        for (int l = 0; l < 3; l++) std::swap(c.lane_stream[l], h->lane_stream[l]);
+        std::swap(c.step_event, h->step_event);
+        std::swap(c.arena, h->arena);
+        std::swap(c.pb, h->pb);
+        std::swap(c.d_params, h->d_params);
+        std::swap(c.h_params, h->h_params);
+        std::swap(c.param_seq, h->param_seq);
+        std::swap(c.cur_thr, h->cur_thr);
+        std::swap(c.cur_nms, h->cur_nms);
+        std::swap(c.graphs, h->graphs);
+        std::swap(c.fence, h->fence);
+    };
+    xchg(h->saved[h->active]);   // park the active state in its slot
+    xchg(h->saved[i]);           // and bring context i in
+    h->active = i;
+}
+}  // namespace
 
 namespace {
 
@@ -763,24 +808,31 @@ void set_params(rf_handle h, float thr, float nms, const uint8_t *input = nullpt
 void destroy(rf_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
-    if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->arena); cudaFree(h->d_weights); cudaFree(h->d_weights_h); cudaFree(h->d_input); cudaFree(h->d_raw); cudaFree(h->d_params);
-    cudaFree(h->pb.cand_keys); cudaFree(h->pb.cand_recs); cudaFree(h->pb.cand_count); cudaFree(h->pb.sort_scratch);
-    cudaFree(h->pb.flag_scratch); cudaFree(h->pb.out_dets); cudaFree(h->pb.out_counts); cudaFree(h->pb.out_total_kept);
+    if (h->saved.empty()) h->saved.resize(1);
+    for (int c = 0; c < (int)h->saved.size(); c++) {
+        switch_ctx(h, c);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
+        h->graphs.clear();
+        cudaFree(h->arena); cudaFree(h->d_params); cudaFreeHost(h->h_params);
+        cudaFree(h->pb.cand_keys); cudaFree(h->pb.cand_recs); cudaFree(h->pb.cand_count); cudaFree(h->pb.sort_scratch);
+        cudaFree(h->pb.flag_scratch); cudaFree(h->pb.out_dets); cudaFree(h->pb.out_counts); cudaFree(h->pb.out_total_kept);
+        for (auto e : h->step_event) if (e) cudaEventDestroy(e);
+        for (int l = 1; l < 3; l++) if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
+        if (h->fence) cudaEventDestroy(h->fence);
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    cudaFree(h->d_weights); cudaFree(h->d_weights_h); cudaFree(h->d_input); cudaFree(h->d_raw);
     for (auto p : h->d_blobs) cudaFree(p);
-    cudaFreeHost(h->h_input); cudaFreeHost(h->h_raw); cudaFreeHost(h->h_params); cudaFreeHost(h->h_dets); cudaFreeHost(h->h_counts);
+    cudaFreeHost(h->h_input); cudaFreeHost(h->h_raw); cudaFreeHost(h->h_dets); cudaFreeHost(h->h_counts);
     for (auto &sl : h->slots) {
         cudaFree(sl.d_in); cudaFreeHost(sl.h_in); cudaFreeHost(sl.h_dets); cudaFreeHost(sl.h_counts);
         if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    for (auto e : h->step_event) if (e) cudaEventDestroy(e);
-    for (int l = 1; l < 3; l++) if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
@@ -891,42 +943,49 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
         if (h->use_tc) CK(tc_init());
         if (h->cfg.precision == RF_PREC_FP32) build_plan<float>(h); else build_plan<__half>(h);
         link_steps(h);
-        for (int l = 1; l < 3; l++) CK(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
-        h->step_event.resize(h->steps.size(), nullptr);
-        for (size_t i = 0; i < h->steps.size(); i++)
-            if (h->steps[i].signals) CK(cudaEventCreateWithFlags(&h->step_event[i], cudaEventDisableTiming));
         place_tensors(h, false);
-        CK(cudaMalloc(&h->arena, h->arena_bytes));
         CK(cudaMalloc(&h->d_weights, h->wstage.size() * sizeof(float)));
         CK(cudaMemcpy(h->d_weights, h->wstage.data(), h->wstage.size() * sizeof(float), cudaMemcpyHostToDevice));
         if (!h->wstage_h.empty()) {
             CK(cudaMalloc(&h->d_weights_h, h->wstage_h.size() * sizeof(__half)));
             CK(cudaMemcpy(h->d_weights_h, h->wstage_h.data(), h->wstage_h.size() * sizeof(__half), cudaMemcpyHostToDevice));
         }
-
         const size_t in_bytes = (size_t)Bm * Hn * Wn * 3;
         CK(cudaMalloc(&h->d_input, in_bytes));
         CK(cudaHostAlloc(&h->h_input, in_bytes, cudaHostAllocDefault));
         h->raw_bytes = (size_t)h->cfg.max_image_w * h->cfg.max_image_h * 3;
         CK(cudaMalloc(&h->d_raw, h->raw_bytes));
         CK(cudaHostAlloc(&h->h_raw, h->raw_bytes, cudaHostAllocDefault));
-        CK(cudaMalloc(&h->d_params, sizeof(PostParams)));
-        CK(cudaHostAlloc(&h->h_params, sizeof(PostParams) * rf_handle_s::kParamSlots, cudaHostAllocDefault));
-
-        PostBuffers &pb = h->pb;
-        pb.anchors_per_image = A; pb.anchors_pow2 = ap2; pb.max_faces = h->cfg.max_faces;
-        CK(cudaMalloc(&pb.cand_keys, sizeof(unsigned long long) * (size_t)Bm * A));
-        CK(cudaMalloc(&pb.cand_recs, sizeof(rf_det) * (size_t)Bm * A));
-        CK(cudaMalloc(&pb.cand_count, sizeof(int) * Bm));
-        CK(cudaMemset(pb.cand_count, 0, sizeof(int) * Bm));
-        CK(cudaMalloc(&pb.sort_scratch, sizeof(unsigned long long) * (size_t)Bm * ap2));
-        CK(cudaMalloc(&pb.flag_scratch, (size_t)Bm * ap2));
-        CK(cudaMalloc(&pb.out_dets, sizeof(rf_det) * (size_t)Bm * pb.max_faces));
-        CK(cudaMalloc(&pb.out_counts, sizeof(int) * Bm));
-        CK(cudaMalloc(&pb.out_total_kept, sizeof(int) * Bm));
-        CK(cudaMemset(pb.out_counts, 0, sizeof(int) * Bm));
-        CK(cudaHostAlloc(&h->h_dets, sizeof(rf_det) * (size_t)Bm * pb.max_faces, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&h->h_dets, sizeof(rf_det) * (size_t)Bm * h->cfg.max_faces, cudaHostAllocDefault));
         CK(cudaHostAlloc(&h->h_counts, sizeof(int) * 2 * Bm, cudaHostAllocDefault));
+        // ---- per-context resources ----
+        h->nctx = h->cfg.streams <= 0 ? 2 : std::min(h->cfg.streams, 4);
+        h->saved.resize(h->nctx);
+        for (int c = 0; c < h->nctx; c++) {
+            switch_ctx(h, c);
+            if (c > 0) CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));   // context 0 keeps the stream created above
+            for (int l = 1; l < 3; l++) CK(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
+            h->step_event.assign(h->steps.size(), nullptr);
+            for (size_t i = 0; i < h->steps.size(); i++)
+                if (h->steps[i].signals) CK(cudaEventCreateWithFlags(&h->step_event[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->fence, cudaEventDisableTiming));
+            CK(cudaMalloc(&h->arena, h->arena_bytes));
+            CK(cudaMalloc(&h->d_params, sizeof(PostParams)));
+            CK(cudaHostAlloc(&h->h_params, sizeof(PostParams) * rf_handle_s::kParamSlots, cudaHostAllocDefault));
+            PostBuffers &pb = h->pb;
+            pb.anchors_per_image = A; pb.anchors_pow2 = ap2; pb.max_faces = h->cfg.max_faces;
+            CK(cudaMalloc(&pb.cand_keys, sizeof(unsigned long long) * (size_t)Bm * A));
+            CK(cudaMalloc(&pb.cand_recs, sizeof(rf_det) * (size_t)Bm * A));
+            CK(cudaMalloc(&pb.cand_count, sizeof(int) * Bm));
+            CK(cudaMemset(pb.cand_count, 0, sizeof(int) * Bm));
+            CK(cudaMalloc(&pb.sort_scratch, sizeof(unsigned long long) * (size_t)Bm * ap2));
+            CK(cudaMalloc(&pb.flag_scratch, (size_t)Bm * ap2));
+            CK(cudaMalloc(&pb.out_dets, sizeof(rf_det) * (size_t)Bm * pb.max_faces));
+            CK(cudaMalloc(&pb.out_counts, sizeof(int) * Bm));
+            CK(cudaMalloc(&pb.out_total_kept, sizeof(int) * Bm));
+            CK(cudaMemset(pb.out_counts, 0, sizeof(int) * Bm));
+        }
+        switch_ctx(h, 0);
         for (int l = 0; l < 3; l++) {
             const int ch[3] = {4, 8, 20};
             for (int k = 0; k < 3; k++) h->blob_elems[3 * l + k] = (size_t)ch[k] * h->lv[l].h * h->lv[l].w;
@@ -953,13 +1012,37 @@ int rf_get_net_size(rf_handle h, int *net_w, int *net_h, int *max_batch, int *ma
     return RF_OK;
 }
 int rf_num_anchors(rf_handle h) { return h ? h->pb.anchors_per_image : RF_ERR_INVALID_ARG; }
-void *rf_stream(rf_handle h) { return h ? (void *)h->stream : nullptr; }
+void *rf_stream(rf_handle h) { if (!h) return nullptr; switch_ctx(h, 0); return (void *)h->stream; }
 
 int rf_synchronize(rf_handle h) {
     if (!h) return RF_ERR_INVALID_ARG;
-    try { CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream)); } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    try {
+        CK(cudaSetDevice(h->device));
+        const int keep = h->active;
+        for (int c = 0; c < h->nctx; c++) { switch_ctx(h, c); CK(cudaStreamSynchronize(h->stream)); }
+        switch_ctx(h, keep);
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
     return RF_OK;
 }
+
+// Orders context 0's stream (the one rf_stream returns) after everything queued so far on every context.
+int rf_fence(rf_handle h) {
+    if (!h) return RF_ERR_INVALID_ARG;
+    try {
+        CK(cudaSetDevice(h->device));
+        switch_ctx(h, 0);
+        cudaStream_t s0 = h->stream;
+        for (int c = 1; c < h->nctx; c++) {
+            switch_ctx(h, c);
+            CK(cudaEventRecord(h->fence, h->stream));
+            CK(cudaStreamWaitEvent(s0, h->fence, 0));
+        }
+        switch_ctx(h, 0);
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+void *rf_last_stream(rf_handle h) { return h ? (void *)(h->last_stream ? h->last_stream : h->stream) : nullptr; }
 
 int rf_launches_per_batch(rf_handle h, int n) {
     (void)n;
@@ -972,6 +1055,8 @@ int rf_detect_batch_device(rf_handle h, const uint8_t *dev_bgr, int n, float thr
     if (rc) return rc;
     try {
         CK(cudaSetDevice(h->device));
+        switch_ctx(h, (int)(h->next_dev_ctx++ % (unsigned)h->nctx));   // consecutive batches overlap on different contexts
+        h->last_stream = h->stream;
         // the caller's device images are read in place (conv0 takes the pointer from the run parameters)
         if (h->param_seq && h->param_seq % rf_handle_s::kParamSlots == 0) CK(cudaStreamSynchronize(h->stream));
         set_params(h, thr, nms, dev_bgr);
@@ -1010,6 +1095,7 @@ int rf_detect_batch(rf_handle h, const uint8_t *const *imgs, const int *widths, 
     const size_t img_bytes = (size_t)Hn * Wn * 3;
     try {
         CK(cudaSetDevice(h->device));
+        switch_ctx(h, 0);
         // Network-sized packed images are copied H2D straight from the caller's memory when it is
         // pinned (cudaHostAlloc / cudaHostRegister / the library's own rf_pinned_input), otherwise via the
         // library's pinned mirror; runs of adjacent sources collapse into one copy.  Other sizes are
@@ -1083,6 +1169,7 @@ int rf_submit_batch(rf_handle h, const uint8_t *const *imgs, int n, float thr, f
     try {
         CK(cudaSetDevice(h->device));
         ensure_slots(h);
+        switch_ctx(h, (int)(h->submit_seq % (unsigned)h->nctx));
         rf_handle_s::Slot &sl = h->slots[h->submit_seq % RF_PIPELINE_DEPTH];
         if (sl.busy) return fail(h, RF_ERR_CAPACITY, "rf_submit_batch: RF_PIPELINE_DEPTH batches already in flight; collect one first");
         // H2D on the copy stream: adjacent sources collapse into one copy
@@ -1154,6 +1241,7 @@ int rf_preprocess(rf_handle h, const uint8_t *bgr, int width, int height, int ro
     const int rs = row_stride ? row_stride : width * 3;
     try {
         CK(cudaSetDevice(h->device));
+        switch_ctx(h, 0);
         CK(cudaStreamSynchronize(h->stream));
         for (int y = 0; y < height; y++) memcpy(h->h_raw + (size_t)y * width * 3, bgr + (size_t)y * rs, (size_t)width * 3);
         CK(cudaMemcpyAsync(h->d_raw, h->h_raw, (size_t)width * height * 3, cudaMemcpyHostToDevice, h->stream));
@@ -1177,6 +1265,7 @@ int rf_forward_heads(rf_handle h, const uint8_t *bgr, int n, float *const heads_
     if (!bgr || !heads_out) return fail(h, RF_ERR_INVALID_ARG, "rf_forward_heads: NULL argument");
     try {
         CK(cudaSetDevice(h->device));
+        switch_ctx(h, 0);
         ensure_blobs(h);
         const size_t bytes = (size_t)n * h->cfg.net_h * h->cfg.net_w * 3;
         CK(cudaStreamSynchronize(h->stream));
@@ -1202,6 +1291,7 @@ int rf_postprocess(rf_handle h, const float *const heads[9], int n, float thr, f
     if (!heads) return fail(h, RF_ERR_INVALID_ARG, "rf_postprocess: NULL heads");
     try {
         CK(cudaSetDevice(h->device));
+        switch_ctx(h, 0);
         ensure_blobs(h);
         for (int i = 0; i < 9; i++)
             CK(cudaMemcpyAsync(h->d_blobs[i], heads[i], sizeof(float) * h->blob_elems[i] * n, cudaMemcpyHostToDevice, h->stream));
@@ -1229,6 +1319,7 @@ int rf_debug_get_tensor(rf_handle h, const char *name, int n, float *out_nchw, i
     if (!out_nchw) return RF_OK;
     try {
         CK(cudaSetDevice(h->device));
+        switch_ctx(h, 0);
         CK(cudaStreamSynchronize(h->stream));
         size_t elems = (size_t)n * t.h * t.w * t.c;
         std::vector<unsigned char> host(elems * h->elem);
@@ -1252,14 +1343,18 @@ int rf_debug_keep_all(rf_handle h) {
     if (!h) return RF_ERR_INVALID_ARG;
     try {
         CK(cudaSetDevice(h->device));
-        CK(cudaStreamSynchronize(h->stream));
-        for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
-        h->graphs.clear();
         for (auto &t : h->tensors) { t.first = -1; t.last = -1; }
         place_tensors(h, true);
-        CK(cudaFree(h->arena));
-        h->arena = nullptr;
-        CK(cudaMalloc(&h->arena, h->arena_bytes));
+        for (int c = 0; c < h->nctx; c++) {
+            switch_ctx(h, c);
+            CK(cudaStreamSynchronize(h->stream));
+            for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
+            h->graphs.clear();
+            CK(cudaFree(h->arena));
+            h->arena = nullptr;
+            CK(cudaMalloc(&h->arena, h->arena_bytes));
+        }
+        switch_ctx(h, 0);
     } catch (const CudaFail &f) { return fail_cuda(h, f); }
     return RF_OK;
 }
@@ -1291,6 +1386,7 @@ int rf_profile_layers(rf_handle h, int n, int iters, char (*names)[64], float *m
     int cnt = 0;
     try {
         CK(cudaSetDevice(h->device));
+        switch_ctx(h, 0);
         set_params(h, h->cur_thr, h->cur_nms);
         run_steps(h, n, h->stream, false);  // warm everything once (also leaves consistent inputs for every step)
         CK(cudaStreamSynchronize(h->stream));
