@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=0, help="execution contexts of the engine (0 = library default 2)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
@@ -226,7 +227,7 @@ def main():
     prec = RF_PREC_FP16 if wl["precision"] == "fp16" else RF_PREC_FP32
     B, H, Wd = wl["batch"], wl["h"], wl["w"]
     eng = Engine(os.path.join(GOLD, "weights", wl["model"] + ".caffemodel"), H, Wd, precision=prec, max_batch=B,
-                 max_faces=128, device=local)
+                 max_faces=128, device=local, streams=args.streams)
     stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=local)
     img_bytes = B * H * Wd * 3
     l2_bytes = 126 * 2**20
@@ -312,10 +313,12 @@ def main():
     fbuf = np.empty((B, eng.max_faces, 15), dtype=np.float32)
     cbuf = np.zeros(B, dtype=np.int32)
 
+    from retinaface_b200.capi import PIPELINE_DEPTH as depth
+
     def pipelined(nsteps, first):
         inflight, nfaces = [], 0
         for i in range(nsteps):
-            if len(inflight) == 3:
+            if len(inflight) == depth:
                 _, c = eng.collect(inflight.pop(0), fbuf, cbuf)
                 nfaces += int(c.sum())
             slot = (first + i) % ring
@@ -360,12 +363,12 @@ def main():
                     step_sum_of_kernels_ms=tot)
         line = dict(metric="faces/sec (end-to-end detect)", value=value, unit="faces/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=dev_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f16" if prec == RF_PREC_FP16 else "f32", data="synthetic", config=dict(config, execution_contexts=2, l2_policy=f"input ring of {ring} batches = {ring * img_bytes / 2**20:.0f} MiB > 2x L2; activations reused in place"),
+                    dtype="f16" if prec == RF_PREC_FP16 else "f32", data="synthetic", config=dict(config, execution_contexts=args.streams or 4, l2_policy=f"input ring of {ring} batches = {ring * img_bytes / 2**20:.0f} MiB > 2x L2; activations reused in place"),
                     images_per_s=K * B * world / (dev_ms * 1e-3), clocks=clocks,
                     e2e=dict(value=e2e_faces / e2e_s, unit="faces/s", h2d_bytes_per_step=img_bytes,
                              d2h_bytes_per_step=B * 4 + B * eng.max_faces * 64, images_per_s=K * B * world / e2e_s,
                              ms_per_step=e2e_s / K * 1e3,
-                             timing="host wall clock around K rf_submit_batch/rf_collect_batch steps, 3 batches in flight",
+                             timing=f"host wall clock around K rf_submit_batch/rf_collect_batch steps, {depth} batches in flight",
                              blocking=dict(value=blk_faces / blk_s, ms_per_step=blk_s / K * 1e3, images_per_s=K * B * world / blk_s,
                                            note="one blocking rf_detect_batch per step (latency mode)")),
                     gpu_launches=K * eng.launches_per_batch(B), launches_per_step=eng.launches_per_batch(B), roofline=roof,

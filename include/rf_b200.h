@@ -74,7 +74,7 @@ typedef struct rf_config {
     int max_image_w, max_image_h;  /* largest caller image (reference: 4096x3072, RetinaFace.cpp:325); 0 -> net size */
     unsigned flags;                /* RF_FLAG_* */
     int streams;                   /* execution contexts the asynchronous entry points rotate through so that
-                                      consecutive batches overlap on the GPU; 0 -> 2, max 4.  The blocking
+                                      consecutive batches overlap on the GPU; 0 -> 4, max 4.  The blocking
                                       rf_detect_batch always uses context 0. */
 } rf_config;
 
@@ -120,7 +120,7 @@ int rf_detect_batch(rf_handle h, const uint8_t *const *bgr_images, const int *wi
  * RF_PIPELINE_DEPTH batches may be in flight, so the H2D copy of batch i+1 overlaps the kernels of
  * batch i (host ingest).  Tickets must be collected in submission order.  Source
  * images may be pinned (copied in place) or pageable (staged through the library's pinned ring). */
-#define RF_PIPELINE_DEPTH 3
+#define RF_PIPELINE_DEPTH 6
 int rf_submit_batch(rf_handle h, const uint8_t *const *bgr_images, int n, float score_threshold, float nms_threshold,
                     int *ticket);
 int rf_collect_batch(rf_handle h, int ticket, rf_face *out_faces, int *out_counts, int32_t *out_anchor_index);
@@ -128,7 +128,9 @@ int rf_collect_batch(rf_handle h, int ticket, rf_face *out_faces, int *out_count
 /* Device-resident variant: `dev_bgr` holds n network-sized u8 BGR HWC images (contiguous) in
  * device memory; results stay on the device: *dev_dets -> [max_batch][max_faces] rf_det,
  * *dev_counts -> [max_batch] int32 (kept count, clamped to max_faces).  Asynchronous on the
- * handle's stream (see rf_stream / rf_synchronize).  This is the buffer a multi-GPU caller
+ * stream of the execution context the call landed on (rf_last_stream; rf_synchronize waits for all).
+ * Consecutive calls rotate over the handle's execution contexts, each with its own output buffers: the
+ * returned pointers stay valid until `streams` further calls.  This is the buffer a multi-GPU caller
  * all-gathers. */
 int rf_detect_batch_device(rf_handle h, const uint8_t *dev_bgr, int n, float score_threshold,
                            float nms_threshold, const rf_det **dev_dets, const int32_t **dev_counts);

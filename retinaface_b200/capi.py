@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 RF_PREC_FP32, RF_PREC_FP16, RF_PREC_INT8 = 0, 1, 2
 RF_FLAG_NO_GRAPH, RF_FLAG_NO_TENSORCORE = 0x1, 0x2
 FACE_FLOATS = 15
+PIPELINE_DEPTH = 6   # RF_PIPELINE_DEPTH
 
 # every symbol include/rf_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
@@ -208,7 +209,7 @@ class Engine:
 
     def submit(self, images: Sequence[np.ndarray], thr: float, nms_thr: float) -> int:
         """Pipelined path: queue one batch of network-sized images (H2D on the copy stream + forward + D2H);
-        returns a ticket for collect().  Up to 3 batches in flight."""
+        returns a ticket for collect().  Up to PIPELINE_DEPTH batches in flight."""
         n = len(images)
         ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in images])
         t = C.c_int()

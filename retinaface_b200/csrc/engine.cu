@@ -959,7 +959,7 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
         CK(cudaHostAlloc(&h->h_dets, sizeof(rf_det) * (size_t)Bm * h->cfg.max_faces, cudaHostAllocDefault));
         CK(cudaHostAlloc(&h->h_counts, sizeof(int) * 2 * Bm, cudaHostAllocDefault));
         // ---- per-context resources ----
-        h->nctx = h->cfg.streams <= 0 ? 2 : std::min(h->cfg.streams, 4);
+        h->nctx = h->cfg.streams <= 0 ? 4 : std::min(h->cfg.streams, 4);
         h->saved.resize(h->nctx);
         for (int c = 0; c < h->nctx; c++) {
             switch_ctx(h, c);

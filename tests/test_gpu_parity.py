@@ -316,25 +316,24 @@ def test_cpp_driver_on_golden_photo(golden_image, tmp_path):
 
 def test_pipelined_submit_collect_equals_blocking(golden_image):
     """rf_submit_batch / rf_collect_batch (H2D of batch i+1 overlapping the kernels of batch i) returns exactly
-    what the blocking rf_detect_batch returns, for pinned and pageable sources, 3 batches in flight."""
+    what the blocking rf_detect_batch returns, RF_PIPELINE_DEPTH batches in flight over 4 execution contexts."""
     from retinaface_b200 import RF_PREC_FP16, RfError
+    from retinaface_b200.capi import PIPELINE_DEPTH
     inp = letterbox_bgr_u8(golden_image, 448, 448)
-    batches = [list(s_real_batch(np.roll(inp, 16 * k, axis=0), 4)) for k in range(7)]
+    batches = [list(s_real_batch(np.roll(inp, 16 * k, axis=0), 4)) for k in range(PIPELINE_DEPTH + 4)]
     eng = _engine("mnet25", 448, 448, RF_PREC_FP16, max_batch=4)
     try:
         want = [eng.detect_batch(b, 0.9, 0.4) for b in batches]
         tickets = []
         got = []
         for k, b in enumerate(batches):
-            if len(tickets) == 3:
+            if len(tickets) == PIPELINE_DEPTH:
                 f, c = eng.collect(tickets.pop(0))
                 got.append([f[i, :c[i]] for i in range(len(c))])
             tickets.append(eng.submit(b, 0.9, 0.4))
+        assert len(tickets) == PIPELINE_DEPTH
         with pytest.raises(RfError):
-            if len(tickets) == 3:
-                eng.submit(batches[0], 0.9, 0.4)      # a 4th batch in flight is refused
-            else:
-                raise RfError(-6, "n/a")
+            eng.submit(batches[0], 0.9, 0.4)          # one more batch in flight is refused
         while tickets:
             f, c = eng.collect(tickets.pop(0))
             got.append([f[i, :c[i]] for i in range(len(c))])
