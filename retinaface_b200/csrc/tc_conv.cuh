@@ -1,27 +1,27 @@
-// tc_conv.cuh -- tcgen05 (5th-gen tensor core) convolution kernels of librf_b200, FP16 in / FP32
-// accumulate in TMEM.  sm_100a only.
+// tc_conv.cuh -- tcgen05 (5th-generation tensor core) convolution kernels of librf_b200: FP16 operands in
+// shared memory, FP32 accumulator in TMEM.  sm_100a only (tcgen05.mma / tcgen05.ld / tcgen05.alloc,
+// cp.async.bulk, mbarrier, griddepcontrol).
 //
-// One kernel template covers the three GEMM-shaped layer families of the network
-// (model/mnet-deconv-0517.prototxt):
-//   TC_PW   : pointwise 1x1 conv                       (rf_c*_lateral / rf_c1_red_conv)
-//   TC_3X3  : full 3x3 conv, pad 1, stride 1           (rf_c*_aggr, SSH det/context convs)
-//   TC_DWPW : depthwise 3x3 (stride 1|2) + BN + ReLU  fused with the following pointwise 1x1
-//             conv + BN + ReLU (mobilenet0_conv{2k-1,2k}, k = 1..13): the depthwise stencil is
-//             evaluated on CUDA cores straight into the shared-memory A operand of the tensor-core
-//             GEMM, so the depthwise activation never touches global memory.
-// GEMM view: D[128 pixels][N] += A[128][K] * W[N][K]^T, K = taps * Cin, one CTA per 128-pixel tile.
-//   A operand: built in shared memory by all 128 threads ("im2col in registers": each thread gathers
-//              16-byte channel groups of the shifted source pixels, or computes the depthwise result)
-//              in the UMMA canonical K-major no-swizzle layout: 8x8 core matrices (8 rows x 16 B),
-//              SBO = 128 B between 8-row groups, LBO = 128*16+16 B between 8-channel groups (the
-//              16 B pad makes the 16-byte shared stores of a quarter-warp conflict free).
-//   B operand: weights pre-packed on the host as the exact shared-memory image of each K chunk and
-//              copied with a single cp.async.bulk (TMA bulk copy, mbarrier complete_tx) per chunk.
-//   MMA      : tcgen05.mma.cta_group::1.kind::f16, M=128, N=Cout (16..256), K=16 per instruction,
-//              issued by one thread; accumulator in TMEM (N fp32 columns x 128 lanes).
-//   Pipeline : 2 shared-memory stages; tcgen05.commit -> mbarrier frees a stage / signals the epilogue.
-//   Epilogue : tcgen05.ld 32x32b (thread = pixel row), + folded-BN bias, ReLU, FP16 pack, 16-byte
-//              stores; output channels may be split over two destinations (SSH concat fusion).
+// Two kernels cover every GEMM-shaped layer of the network (model/mnet-deconv-0517.prototxt):
+//   k_tc_conv_staged : 1x1 and 3x3 (pad 1) convolutions -- rf_c*_lateral / rf_c1_red_conv, rf_c*_aggr, the SSH
+//                      det/context convs (branches that share an input run as one conv, outputs split);
+//                      UPADD variant: the FPN merge (deconv-upsample + crop + add) fused into the staging.
+//   k_tc_dwpw_staged : depthwise 3x3 (stride 1|2) + BN + ReLU fused with the following pointwise 1x1 + BN +
+//                      ReLU (mobilenet0_conv3..conv26): the stencil runs on CUDA cores from shared memory
+//                      straight into the A operand of the tensor-core GEMM.
+// GEMM view: D[128 rows][N] (+)= A[128][K] * W[N][K]^T, one CTA (256 threads) per 128-row tile.
+//   Operand layout : UMMA canonical K-major, no swizzle: 8x8 core matrices (8 rows x 16 B), SBO = 128 B between
+//                    8-row groups, LBO between 8-channel groups (odd multiple of 16 B, so 16-byte shared stores of
+//                    a quarter-warp never conflict).  Descriptors: cute::UMMA::SmemDescriptor, version 1.
+//   A operand      : "staged range + shifted descriptors", see below -- no im2col, not even in shared memory.
+//   B operand      : weights pre-packed on the host as the exact shared-memory image, fetched by ONE TMA bulk
+//                    copy (cp.async.bulk ... mbarrier::complete_tx) per CTA, issued before griddepcontrol.wait so
+//                    it overlaps the previous kernel (programmatic dependent launch).
+//   MMA            : tcgen05.mma.cta_group::1.kind::f16, M = 128, N = Cout (16..256), K = 16 per instruction,
+//                    issued by one thread; tcgen05.commit -> mbarrier signals the epilogue.
+//   Epilogue       : tcgen05.ld 32x32b.x16 (thread = GEMM row, 8 warps = 4 lane quadrants x 2 column halves),
+//                    + folded-BN bias (shared memory), ReLU, FP16 pack, 16-byte stores; the output channels may
+//                    be split over two destinations with their own pixel stride (Concat + ReLU fusion).
 #pragma once
 #include "common.cuh"
 
