@@ -44,6 +44,10 @@ WORKLOADS = {
     "mnet25_fp32_b8_448": dict(model="mnet25", precision="fp32", batch=8, h=448, w=448),
     "mnet25_fp16_b1_448": dict(model="mnet25", precision="fp16", batch=1, h=448, w=448),
     "mnet25_fp16_b32_448": dict(model="mnet25", precision="fp16", batch=32, h=448, w=448),
+    # configs[2]: INT8 with the reference's TensorRT calibration table
+    "mnet0517_int8_b32_448": dict(model="mnet-deconv-0517", precision="int8", batch=32, h=448, w=448),
+    "mnet0517_int8_b8_448": dict(model="mnet-deconv-0517", precision="int8", batch=8, h=448, w=448),
+    "mnet0517_fp16_b32_448": dict(model="mnet-deconv-0517", precision="fp16", batch=32, h=448, w=448),
     # configs[3]: large input / many-anchor NMS stress
     "mnet25_fp16_b8_1280x896": dict(model="mnet25", precision="fp16", batch=8, h=896, w=1280),
 }
@@ -223,11 +227,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from retinaface_b200 import RF_PREC_FP16, RF_PREC_FP32, Engine
-    prec = RF_PREC_FP16 if wl["precision"] == "fp16" else RF_PREC_FP32
+    from retinaface_b200 import RF_PREC_FP16, RF_PREC_FP32, RF_PREC_INT8, Engine
+    prec = {"fp16": RF_PREC_FP16, "fp32": RF_PREC_FP32, "int8": RF_PREC_INT8}[wl["precision"]]
     B, H, Wd = wl["batch"], wl["h"], wl["w"]
     eng = Engine(os.path.join(GOLD, "weights", wl["model"] + ".caffemodel"), H, Wd, precision=prec, max_batch=B,
-                 max_faces=128, device=local, streams=args.streams)
+                 max_faces=128, device=local, streams=args.streams,
+                 int8_table=os.path.join(GOLD, "weights", wl["model"] + ".table.int8") if prec == RF_PREC_INT8 else None)
     stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=local)
     img_bytes = B * H * Wd * 3
     l2_bytes = 126 * 2**20
@@ -363,7 +368,7 @@ def main():
                     step_sum_of_kernels_ms=tot)
         line = dict(metric="faces/sec (end-to-end detect)", value=value, unit="faces/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=dev_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f16" if prec == RF_PREC_FP16 else "f32", data="synthetic", config=dict(config, execution_contexts=args.streams or 4, l2_policy=f"input ring of {ring} batches = {ring * img_bytes / 2**20:.0f} MiB > 2x L2; activations reused in place"),
+                    dtype={RF_PREC_FP16: "f16", RF_PREC_FP32: "f32", RF_PREC_INT8: "s8"}[prec], data="synthetic", config=dict(config, execution_contexts=args.streams or 4, l2_policy=f"input ring of {ring} batches = {ring * img_bytes / 2**20:.0f} MiB > 2x L2; activations reused in place"),
                     images_per_s=K * B * world / (dev_ms * 1e-3), clocks=clocks,
                     e2e=dict(value=e2e_faces / e2e_s, unit="faces/s", h2d_bytes_per_step=img_bytes,
                              d2h_bytes_per_step=B * 4 + B * eng.max_faces * 64, images_per_s=K * B * world / e2e_s,

@@ -33,6 +33,17 @@ template <> struct Vec8<__half> {
     }
 };
 
+// int8 activations (INT8 path): 8 consecutive channels = 8 bytes; to_float yields the raw integer values, the
+// caller applies the tensor's scale.
+template <> struct Vec8<int8_t> {
+    uint2 v;
+    __device__ __forceinline__ void load(const int8_t *p) { v = *reinterpret_cast<const uint2 *>(p); }
+    __device__ __forceinline__ void to_float(float f[8]) const {
+        f[0] = (float)(int8_t)(v.x & 0xff); f[1] = (float)(int8_t)((v.x >> 8) & 0xff); f[2] = (float)(int8_t)((v.x >> 16) & 0xff); f[3] = (float)(int8_t)(v.x >> 24);
+        f[4] = (float)(int8_t)(v.y & 0xff); f[5] = (float)(int8_t)((v.y >> 8) & 0xff); f[6] = (float)(int8_t)((v.y >> 16) & 0xff); f[7] = (float)(int8_t)(v.y >> 24);
+    }
+};
+
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
 template <typename T> __device__ __forceinline__ T from_f(float x);

@@ -284,8 +284,10 @@ namespace rf {
 // ------------------------------------------------------------------------------------------
 struct StemWeights { const float *w0, *b0, *wd, *bd, *wp, *bp; };
 
-__global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ run, __half *__restrict__ out, StemWeights sw,
-                                              int n, int H, int W) {
+// OutT = __half (FP16 path) or int8_t (INT8 path: the result is quantised with out_inv_scale = 1/s(relu2)).
+template <typename OutT>
+__global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ run, OutT *__restrict__ out, StemWeights sw,
+                                              int n, int H, int W, float out_inv_scale) {
     __shared__ __align__(4) uint8_t s_in[37][116];   // input patch rows: `mis` alignment bytes + 37 px * 3 B, as 29 words
     __shared__ __align__(16) float s_c0[18 * 18][8];
     __shared__ __align__(16) float s_w0[27 * 8 + 8];
@@ -393,12 +395,28 @@ __global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ 
     }
 #pragma unroll
     for (int j = 0; j < 16; j++) o[j] = fmaxf(o[j], 0.f);
-    Vec8<__half> v0, v1;
-    v0.from_float(o);
-    v1.from_float(o + 8);
-    __half *dst = out + (((size_t)b * OH + oy) * OW + ox) * 16;
-    v0.store(dst);
-    v1.store(dst + 8);
+    OutT *dst = out + (((size_t)b * OH + oy) * OW + ox) * 16;
+    if constexpr (sizeof(OutT) == 2) {
+        Vec8<__half> v0, v1;
+        v0.from_float(o);
+        v1.from_float(o + 8);
+        v0.store(reinterpret_cast<__half *>(dst));
+        v1.store(reinterpret_cast<__half *>(dst) + 8);
+    } else {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int q = __float2int_rn(__fmul_rn(o[j4 * 4 + k], out_inv_scale));
+                q = max(-127, min(127, q));
+                w |= (uint32_t)(q & 0xff) << (8 * k);
+            }
+            pk[j4] = w;
+        }
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
 }
 
 }  // namespace rf
@@ -451,6 +469,66 @@ __global__ void __launch_bounds__(256) k_fpn_merge_h2(const __half *__restrict__
         for (int c = 0; c < 4; c++) acc[c] = __hfma2(u2[c], w2[c], acc[c]);
     }
     *reinterpret_cast<uint4 *>(out + (size_t)pix * C + c0) = accv;
+}
+
+}  // namespace rf
+
+namespace rf {
+
+// FPN merge, INT8 path (c1 level): out_q = rint(q_lat * (s_lat/s_out) + sum_taps q_up * (w * s_up/s_out)), one thread per
+// (pixel, 16 channels).  wq: [16 taps][C] floats.
+__global__ void __launch_bounds__(256) k_fpn_merge_i8(const int8_t *__restrict__ lateral, const int8_t *__restrict__ up, int8_t *__restrict__ out,
+                                                      const float *__restrict__ wq, float lat_mul, int n, int H, int W, int C) {
+    pdl_trigger();
+    const int cg = C >> 4, UH = H >> 1, UW = W >> 1;
+    const long total = (long)n * H * W * cg;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % cg);
+    const long pix = idx / cg;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+    const int c0 = g * 16;
+    const int i_hi = (y + 1) >> 1, j_hi = (x + 1) >> 1;
+    pdl_wait();
+    auto unpack = [](const uint4 &v, float f[16]) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            f[4 * i + 0] = (float)(int8_t)(w[i] & 0xff); f[4 * i + 1] = (float)(int8_t)((w[i] >> 8) & 0xff);
+            f[4 * i + 2] = (float)(int8_t)((w[i] >> 16) & 0xff); f[4 * i + 3] = (float)(int8_t)(w[i] >> 24);
+        }
+    };
+    float acc[16];
+    unpack(*reinterpret_cast<const uint4 *>(lateral + (size_t)pix * C + c0), acc);
+#pragma unroll
+    for (int c = 0; c < 16; c++) acc[c] = __fmul_rn(acc[c], lat_mul);
+#pragma unroll
+    for (int di = 0; di < 2; di++) {
+        const int i = i_hi - di, ky = y - 2 * i + 1;
+        if (i < 0 || i >= UH) continue;
+#pragma unroll
+        for (int dj = 0; dj < 2; dj++) {
+            const int j = j_hi - dj, kx = x - 2 * j + 1;
+            if (j < 0 || j >= UW) continue;
+            float u[16];
+            unpack(*reinterpret_cast<const uint4 *>(up + (((size_t)b * UH + i) * UW + j) * C + c0), u);
+            const float *w = wq + (ky * 4 + kx) * C + c0;
+#pragma unroll
+            for (int c = 0; c < 16; c++) acc[c] = __fadd_rn(acc[c], __fmul_rn(u[c], __ldg(w + c)));   // no FMA: bit-identical to the integer oracle
+        }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; j4++) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int q = max(-127, min(127, __float2int_rn(acc[j4 * 4 + k])));
+            w |= (uint32_t)(q & 0xff) << (8 * k);
+        }
+        pk[j4] = w;
+    }
+    *reinterpret_cast<uint4 *>(out + (size_t)pix * C + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
 }  // namespace rf

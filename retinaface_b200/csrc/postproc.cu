@@ -110,6 +110,11 @@ __global__ void __launch_bounds__(128) k_head_decode(HeadLaunch L, int net_w, in
         v.load(f + g * 8);
         v.to_float(&x[g * 8]);
     }
+    if (sizeof(T) == 1) {                 // int8 features: dequantise with the concat tensor's scale
+        const float sc = L.hw[l].in_scale;
+#pragma unroll
+        for (int c = 0; c < 64; c++) x[c] = __fmul_rn(x[c], sc);
+    }
     auto dot = [&](int o) -> float {
         float acc = sb[o];
         const float4 *w4 = reinterpret_cast<const float4 *>(&sw[o * 64]);
@@ -342,6 +347,8 @@ void launch_head_decode(const T *const feat[3], const HeadWeights hw[3], const L
 template void launch_head_decode<float>(const float *const[3], const HeadWeights[3], const LevelDesc[3], int, int, int,
                                         const PostParams *, const PostBuffers &, float *const[9], cudaStream_t);
 template void launch_head_decode<__half>(const __half *const[3], const HeadWeights[3], const LevelDesc[3], int, int, int,
+                                         const PostParams *, const PostBuffers &, float *const[9], cudaStream_t);
+template void launch_head_decode<int8_t>(const int8_t *const[3], const HeadWeights[3], const LevelDesc[3], int, int, int,
                                          const PostParams *, const PostBuffers &, float *const[9], cudaStream_t);
 
 void launch_blob_decode(const float *const blobs[9], const LevelDesc lv[3], int n, int net_w, int net_h,

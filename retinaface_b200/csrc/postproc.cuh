@@ -22,6 +22,7 @@ struct PostBuffers {
 struct HeadWeights {
     const float *w;     // [32][64]: rows 0-3 cls_score, 4-11 bbox_pred, 12-31 landmark_pred
     const float *b;     // [32]
+    float in_scale;     // 1 for float/half features; the concat tensor's quantisation scale for int8 features
 };
 
 // Fused per-level predictor + decode: 1x1 convs (cls 4, bbox 8, landmark 20), the 2-way softmax,

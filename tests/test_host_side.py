@@ -28,8 +28,9 @@ def test_product_has_no_oracle_dependency():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(root, f), errors="ignore").read()
-                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
-                assert "liboracle" not in src and "oracle/" not in src.replace("oracle/__init__", ""), f
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f          # no python import
+                assert not re.search(r"#\s*include\s*[<\"][^>\"]*oracle", src), f             # no C/C++ include
+                assert "liboracle" not in src and "libref_postproc" not in src and "oracle/_ref" not in src, f   # no link / dlopen
 
 
 def test_model_front_end_matches_oracle_fold(built_lib):
