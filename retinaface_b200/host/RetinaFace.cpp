@@ -9,7 +9,9 @@ RetinaFace::RetinaFace(string &model, string network_, float nms, const RetinaFa
     if (network != "net3") throw std::runtime_error("network setting error " + network + ": only net3 is configured");
     const string path = model + "/" + opt_.model_file;
     rf_config cfg{};
+    const string table = model + "/" + opt_.int8_table_file;
     cfg.caffemodel_path = path.c_str();
+    cfg.int8_table_path = opt_.precision == RF_PREC_INT8 ? table.c_str() : nullptr;
     cfg.precision = opt_.precision;
     cfg.net_w = opt_.net_w;
     cfg.net_h = opt_.net_h;

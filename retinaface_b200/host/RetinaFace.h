@@ -35,6 +35,7 @@ struct RetinaFaceOptions {
     int device = 0;
     int max_image_w = 4096, max_image_h = 3072;   // RetinaFace.cpp:325
     string model_file = "mnet-deconv-0517.caffemodel";   // RetinaFace.cpp:276
+    string int8_table_file = "mnet-deconv-0517.table.int8";   // used when precision == RF_PREC_INT8 (trtnetbase.cpp:13)
 };
 
 class RetinaFace {

@@ -72,3 +72,28 @@ def test_committed_fixtures_are_the_reference_files():
     for f in ("mnet25.caffemodel", "mnet-deconv-0517.caffemodel", "mnet-deconv-0517.table.int8"):
         assert filecmp.cmp(f"{REFERENCE}/model/{f}", os.path.join(GOLDEN, "weights", f), shallow=False)
     assert filecmp.cmp(f"{REFERENCE}/data/img.jpg", os.path.join(GOLDEN, "data", "img.jpg"), shallow=False)
+
+
+def test_int8_oracle_within_calibration_tolerance_of_fp32(golden_image):
+    """The integer scheme (oracle/mnet_int8.py: table scales + per-channel weight scales) against the FP32
+    oracle on the golden photo: per-tensor RMS error of a few LSB, same 5 faces, boxes within 2 px."""
+    from conftest import WEIGHTS
+    from oracle.mnet_int8 import Int8Oracle, read_table
+    from oracle.postproc import PostprocOracle
+    table = os.path.join(WEIGHTS, "mnet-deconv-0517.table.int8")
+    t = read_table(table)
+    assert len(t) == 210 and abs(t["data"] - 2.00836) < 1e-4          # SURVEY.md Appendix C
+    inp = letterbox_bgr_u8(golden_image, 448, 448)
+    o8 = Int8Oracle(caffemodel("mnet-deconv-0517"), table)
+    blobs, tens = o8.forward(inp[None], want_tensors=True)
+    ref = MnetOracle(caffemodel("mnet-deconv-0517")).forward(preprocess_bgr_u8(inp), want=list(tens.keys()))
+    for name, (q, s) in tens.items():
+        rms = np.sqrt(np.mean((q.astype(np.float32) * np.float32(s) - ref[name]) ** 2)) / s
+        assert rms < 4.0, (name, rms)
+    po = PostprocOracle()
+    r8 = po.postprocess([b[0] for b in blobs], 448, 448, 0.9, 0.4)["faces"]
+    gold = np.load(os.path.join(GOLDEN, "dets_mnet-deconv-0517_448x448.npz"))["faces_thr0.9"]
+    assert len(r8) == len(gold) == 5
+    for g in gold:
+        c = r8[np.argmin(np.abs(r8[:, 1:3] - g[1:3]).sum(1))]
+        assert np.abs(c[1:5] - g[1:5]).max() < 2.0 and abs(c[0] - g[0]) < 0.03
