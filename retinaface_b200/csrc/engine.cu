@@ -219,7 +219,6 @@ struct Builder {
         h->tensor_by_name[name] = (int)h->tensors.size() - 1;
         return (int)h->tensors.size() - 1;
     }
-    void alias(const std::string &name, int id) { h->tensor_by_name[name] = id; }
     void step(Step s) { h->steps.push_back(std::move(s)); }
 };
 

@@ -385,3 +385,34 @@ def test_int8_engine_vs_integer_oracle(golden_image, post_oracle):
             assert np.abs(c[1:5] - g[1:5]).max() < 2.0 and abs(c[0] - g[0]) < 0.03, (c[:5], g[:5])
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp16", "int8"])
+def test_large_input_and_odd_batches(prec, golden_image, post_oracle):
+    """configs[3]-style input (1280x896, 47,040 anchors/image) and batch sizes that make tiles straddle image
+    boundaries (1, 3, max_batch): tensor-core engines against the FP32 golden detections of the same model, and
+    every batch element against its own heads through the oracle post-process (selection bit-exact)."""
+    from retinaface_b200 import RF_PREC_FP16, RF_PREC_INT8, Engine
+    model = "mnet-deconv-0517"
+    table = os.path.join(GOLDEN, "weights", model + ".table.int8")
+    h, w = 896, 1280
+    inp = letterbox_bgr_u8(golden_image, h, w)
+    eng = Engine(caffemodel(model), h, w, precision=RF_PREC_FP16 if prec == "fp16" else RF_PREC_INT8, max_batch=3,
+                 int8_table=table if prec == "int8" else None)
+    try:
+        gold = np.load(os.path.join(GOLDEN, f"dets_{model}_{h}x{w}.npz"))["faces_thr0.9"]
+        tol_px, tol_s = (1.0, 1e-2) if prec == "fp16" else (4.0, 0.05)
+        for n in (1, 3, 2):
+            batch = [inp] + [np.roll(inp, 32 * k, axis=1) for k in range(1, n)]
+            faces, idx = eng.detect_batch(batch, 0.9, 0.4, want_index=True)
+            assert len(faces[0]) == len(gold), (prec, n, len(faces[0]), len(gold))
+            for g in gold:
+                c = faces[0][np.argmin(np.abs(faces[0][:, 1:3] - g[1:3]).sum(1))]
+                assert np.abs(c[1:5] - g[1:5]).max() < tol_px and abs(c[0] - g[0]) < tol_s, (prec, n, c[:5], g[:5])
+            heads = eng.forward_heads(np.stack(batch))
+            for i in range(n):
+                ref = post_oracle.postprocess([x[i] for x in heads], h, w, 0.9, 0.4)
+                _compare_dets(faces[i], idx[i], ref, f"{prec} n={n} img={i}")
+                assert len(faces[i]) >= 5
+    finally:
+        eng.close()
