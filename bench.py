@@ -171,7 +171,25 @@ def cpu_measure(wl, batches, budget_s, min_steps=2):
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else this process (or NCCL / a library) prints was
+    redirected to stderr at start-up, so stdout carries exactly one line."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)            # e.g. "NCCL version ..." banners must not precede the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -217,7 +235,7 @@ def main():
                                       sample=f"{steps} steps x {wl['batch']} images: cv2.dnn FP32 forward + oracle/postproc.c "
                                              "(the reference's CPU-Caffe path cannot be built: Caffe/OpenCV C++ absent)"),
                     e2e=dict(value=v, unit="faces/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -385,7 +403,7 @@ def main():
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     eng_close()
     if world > 1:
         dist.barrier()
