@@ -379,8 +379,14 @@ def main():
         top = max(prof, key=lambda p: p["ms"])
         ach_gbs = top["bytes"] / (top["ms"] * 1e-3) / 1e9
         ach_tf = top["flops"] / (top["ms"] * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):            # dram__bytes_read+write of the dominant kernel from the committed ncu --set full capture
+            tj = json.load(open(tp))
+            if tj.get("workload") == args.workload and tj.get("kernel") == top["name"]:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         roof = dict(bound="hbm", kernel=top["name"], achieved=ach_gbs, peak=pk["hbm_gbs"], unit="GB/s", frac=ach_gbs / pk["hbm_gbs"],
-                    traffic=None, peak_source=pk["src"], kernel_ms=top["ms"], kernel_share_of_step=top["ms"] / tot,
+                    traffic=traffic, peak_source=pk["src"], kernel_ms=top["ms"], kernel_share_of_step=top["ms"] / tot,
                     tensor_tflops=ach_tf, tensor_frac=ach_tf / pk["bf16_tflops"],
                     step_algorithmic_gb=sum(p["bytes"] for p in prof) / 1e9, step_algorithmic_gflop=sum(p["flops"] for p in prof) / 1e9,
                     step_sum_of_kernels_ms=tot)
