@@ -167,6 +167,15 @@ int rf_launches_per_batch(rf_handle h, int n);
  * batch n: fills up to cap entries, returns the count.  For bench.py's roofline line. */
 int rf_profile_layers(rf_handle h, int n, int iters, char (*names)[64], float *ms, double *bytes, double *flops, int cap);
 
+/* INT8 entropy calibration -- replaces the reference's offline INT8-Calibration-Tool (calibrationtable.cpp:399-583):
+ * runs the n network-sized u8 BGR host images through an RF_PREC_FP32 handle twice (absmax, then 2048-bin histograms of
+ * every activation tensor), searches the KL-optimal clipping threshold per tensor and writes a table in the reference's
+ * own TensorRT cache format ("TRT-5102-EntropyCalibration2", one "<caffe top>: <hex float32 scale>" line per tensor) that
+ * rf_create(RF_PREC_INT8) -- or the reference's Int8EntropyCalibrator2 reader (trtnetbase.cpp:31-44) -- consumes. */
+int rf_calibrate_int8(rf_handle h, const uint8_t *bgr_net_sized, int n_images, const char *out_table_path);
+/* Host-only: the threshold search of the calibrator on one histogram (returns the threshold in bins). */
+double rf_kl_threshold_bins(const unsigned *hist, int bins, int levels);
+
 /* Debug / parity aids (not part of the drop-in surface): fetch a materialised activation by its
  * Caffe top name (e.g. "mobilenet0_relu10_fwd", "_plus0", "rf_c1_det_concat_relu") as NCHW
  * float32 after a forward; rf_debug_keep_all disables activation-buffer reuse so every tensor

@@ -19,6 +19,7 @@ SOURCES = [
     ("engine.cu", []),
     ("postproc.cu", ["-fmad=false"]),
     ("preprocess.cu", ["-fmad=false"]),
+    ("calibrate.cu", []),
     ("model.cpp", []),
 ]
 

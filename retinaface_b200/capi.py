@@ -20,7 +20,7 @@ EXPORTS = [
     "rf_abi_version", "rf_build_info", "rf_status_string", "rf_create", "rf_destroy", "rf_last_error",
     "rf_pinned_input", "rf_device_input", "rf_detect_batch", "rf_submit_batch", "rf_collect_batch", "rf_detect_batch_device", "rf_forward_heads",
     "rf_postprocess", "rf_preprocess", "rf_get_net_size", "rf_num_anchors", "rf_stream", "rf_synchronize", "rf_fence", "rf_last_stream",
-    "rf_launches_per_batch", "rf_profile_layers", "rf_debug_get_tensor", "rf_debug_keep_all", "rf_model_inspect",
+    "rf_launches_per_batch", "rf_profile_layers", "rf_debug_get_tensor", "rf_debug_keep_all", "rf_model_inspect", "rf_calibrate_int8", "rf_kl_threshold_bins",
 ]
 
 
@@ -86,6 +86,9 @@ def load_library() -> C.CDLL:
     lib.rf_profile_layers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.rf_debug_get_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p] + [C.POINTER(C.c_int)] * 3
     lib.rf_debug_keep_all.argtypes = [C.c_void_p]
+    lib.rf_calibrate_int8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p]
+    lib.rf_kl_threshold_bins.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.rf_kl_threshold_bins.restype = C.c_double
     _lib = lib
     return lib
 
@@ -105,6 +108,13 @@ def model_inspect(caffemodel: str, layer: str):
     if rc != 0:
         raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
     return w, b
+
+
+def kl_threshold_bins(hist: np.ndarray, levels: int = 128) -> float:
+    """The calibrator's threshold search (host-only entry point of the library)."""
+    lib = load_library()
+    h = np.ascontiguousarray(hist, dtype=np.uint32)
+    return float(lib.rf_kl_threshold_bins(h.ctypes.data_as(C.c_void_p), len(h), levels))
 
 
 STRIDES = (32, 16, 8)
@@ -262,6 +272,12 @@ class Engine:
         out = np.empty((self.net_h, self.net_w, 3), dtype=np.uint8)
         self._check(self.lib.rf_preprocess(self.h, img.ctypes.data, img.shape[1], img.shape[0], 0, out.ctypes.data))
         return out
+
+    def calibrate_int8(self, images: np.ndarray, out_table: str):
+        """INT8 entropy calibration on an RF_PREC_FP32 engine; writes a TensorRT-format table."""
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        assert images.shape[1:] == (self.net_h, self.net_w, 3)
+        self._check(self.lib.rf_calibrate_int8(self.h, images.ctypes.data, images.shape[0], out_table.encode()))
 
     def debug_keep_all(self):
         self._check(self.lib.rf_debug_keep_all(self.h))

@@ -15,6 +15,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "calibrate.cuh"
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "model.h"
@@ -1703,6 +1704,74 @@ int rf_debug_keep_all(rf_handle h) {
     } catch (const CudaFail &f) { return fail_cuda(h, f); }
     return RF_OK;
 }
+
+// INT8 entropy calibration (replaces INT8-Calibration-Tool/calibrationtable.cpp:399-583).  `h` must be an
+// RF_PREC_FP32 handle (its SIMT plan materialises every tensor the INT8 plan quantises, including the depthwise outputs
+// and the FPN sums).  Two passes over the n network-sized images: absmax, then 2048-bin histograms; then the KL threshold
+// search per tensor on the host; the table is written in the reference's TensorRT cache format.
+int rf_calibrate_int8(rf_handle h, const uint8_t *bgr_net_sized, int n_images, const char *out_table_path) {
+    if (!h || !bgr_net_sized || n_images <= 0 || !out_table_path) return fail(h, RF_ERR_INVALID_ARG, "rf_calibrate_int8: bad arguments");
+    if (h->cfg.precision != RF_PREC_FP32) return fail(h, RF_ERR_UNSUPPORTED, "rf_calibrate_int8: create the handle with RF_PREC_FP32 (every tensor must be materialised)");
+    const size_t img_bytes = (size_t)h->cfg.net_h * h->cfg.net_w * 3;
+    const int T = (int)h->tensors.size();
+    float *d_max = nullptr;
+    unsigned *d_hist = nullptr;
+    try {
+        CK(cudaSetDevice(h->device));
+        int rc = rf_debug_keep_all(h);
+        if (rc) return rc;
+        switch_ctx(h, 0);
+        CK(cudaMalloc(&d_max, sizeof(float) * T));
+        CK(cudaMalloc(&d_hist, sizeof(unsigned) * (size_t)T * CALIB_BINS));
+        CK(cudaMemsetAsync(d_max, 0, sizeof(float) * T, h->stream));
+        CK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * (size_t)T * CALIB_BINS, h->stream));
+        std::vector<float> hmax(T, 0.f);
+        for (int pass = 0; pass < 2; pass++) {
+            for (int i0 = 0; i0 < n_images; i0 += h->cfg.max_batch) {
+                const int n = std::min(h->cfg.max_batch, n_images - i0);
+                CK(cudaStreamSynchronize(h->stream));
+                memcpy(h->h_input, bgr_net_sized + (size_t)i0 * img_bytes, (size_t)n * img_bytes);
+                CK(cudaMemcpyAsync(h->d_input, h->h_input, (size_t)n * img_bytes, cudaMemcpyHostToDevice, h->stream));
+                set_params(h, h->cur_thr, h->cur_nms);
+                run_steps(h, n, h->stream, false);
+                for (int t = 0; t < T; t++) {
+                    const TensorInfo &ti = h->tensors[t];
+                    const size_t elems = (size_t)n * ti.h * ti.w * ti.c;
+                    const float *x = reinterpret_cast<const float *>(h->tptr(t));
+                    if (pass == 0) launch_absmax<float>(x, elems, d_max + t, h->stream);
+                    else if (hmax[t] > 0.f) launch_hist<float>(x, elems, (float)CALIB_BINS / hmax[t], d_hist + (size_t)t * CALIB_BINS, h->stream);
+                }
+                CK(cudaGetLastError());
+            }
+            if (pass == 0) {
+                CK(cudaMemcpyAsync(hmax.data(), d_max, sizeof(float) * T, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+            }
+        }
+        std::vector<unsigned> hist((size_t)T * CALIB_BINS);
+        CK(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned) * hist.size(), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(d_max); cudaFree(d_hist);
+        d_max = nullptr; d_hist = nullptr;
+        std::vector<std::pair<std::string, float>> scales;
+        scales.emplace_back("data", 255.0f / 127.0f);          // u8 input range; the engine consumes the u8 image directly
+        for (int t = 0; t < T; t++) {
+            if (hmax[t] <= 0.f) { scales.emplace_back(h->tensors[t].name, 1.0f / 127.0f); continue; }
+            const double bins = kl_threshold_bins(hist.data() + (size_t)t * CALIB_BINS);
+            const double thr = bins * (double)hmax[t] / CALIB_BINS;
+            scales.emplace_back(h->tensors[t].name, (float)(thr / 127.0));
+        }
+        std::string err;
+        if (!write_int8_table(out_table_path, scales, err)) return fail(h, RF_ERR_IO, err);
+    } catch (const CudaFail &f) {
+        cudaFree(d_max); cudaFree(d_hist);
+        return fail_cuda(h, f);
+    }
+    return RF_OK;
+}
+
+// Host-only: the KL threshold search on a caller-supplied histogram (for CPU-side tests of the calibrator).
+double rf_kl_threshold_bins(const unsigned *hist, int bins, int levels) { return kl_threshold_bins(hist, bins, levels); }
 
 // Host-only (no GPU needed): folded FP32 weights/bias of one convolution as the engine will hold
 // them (BatchNorm + Scale + bias folded).  dims = {cout, cin/groups, k, k}.  Lets CPU-only tests

@@ -416,3 +416,37 @@ def test_large_input_and_odd_batches(prec, golden_image, post_oracle):
                 assert len(faces[i]) >= 5
     finally:
         eng.close()
+
+
+def test_int8_calibrator_end_to_end(golden_image, tmp_path):
+    """rf_calibrate_int8 on an FP32 engine writes a TensorRT-format table for *mnet25* (the reference ships a
+    table only for mnet-deconv-0517); an INT8 engine created from that table then reproduces the FP32 golden detections
+    within the calibration tolerance.  Also: on mnet-deconv-0517 the scales it finds are of the same magnitude as the
+    shipped TensorRT table's (different calibration images, same method family)."""
+    from oracle.mnet_int8 import read_table
+    from retinaface_b200 import RF_PREC_FP32, RF_PREC_INT8, Engine
+    inp = letterbox_bgr_u8(golden_image, 448, 448)
+    calib = np.stack([np.roll(np.roll(inp, 16 * k, axis=1), 8 * (k % 3), axis=0) for k in range(8)] + [inp[:, ::-1].copy()])
+    for model in ("mnet25", "mnet-deconv-0517"):
+        table = str(tmp_path / f"{model}.table.int8")
+        fp32 = Engine(caffemodel(model), 448, 448, precision=RF_PREC_FP32, max_batch=4)
+        try:
+            fp32.calibrate_int8(calib, table)
+        finally:
+            fp32.close()
+        t = read_table(table)
+        assert open(table).readline().strip() == "TRT-5102-EntropyCalibration2" and len(t) >= 44
+        if model == "mnet-deconv-0517":
+            shipped = read_table(os.path.join(GOLDEN, "weights", "mnet-deconv-0517.table.int8"))
+            ratios = np.array([t[k] / shipped[k] for k in t if k in shipped and k != "data"])
+            assert len(ratios) >= 40 and 0.5 < np.median(ratios) < 2.0 and (np.abs(np.log2(ratios)) < 2).mean() > 0.9, np.median(ratios)
+        eng = Engine(caffemodel(model), 448, 448, precision=RF_PREC_INT8, max_batch=2, int8_table=table)
+        try:
+            faces = eng.detect_batch([inp], 0.9, 0.4)[0]
+            gold = np.load(os.path.join(GOLDEN, f"dets_{model}_448x448.npz"))["faces_thr0.9"]
+            assert len(faces) == len(gold) == 5
+            for g in gold:
+                c = faces[np.argmin(np.abs(faces[:, 1:3] - g[1:3]).sum(1))]
+                assert np.abs(c[1:5] - g[1:5]).max() < 3.0 and abs(c[0] - g[0]) < 0.05, (model, c[:5], g[:5])
+        finally:
+            eng.close()

@@ -85,3 +85,20 @@ def test_cpp_driver_builds_and_fails_loudly_without_gpu(built_lib):
         pytest.skip("GPU present: covered by the gpu test")
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "weights"), "--iters", "1"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "no CPU path" in r.stderr
+
+
+def test_calibrator_threshold_search_matches_numpy_restatement(built_lib):
+    """Host-side part of rf_calibrate_int8: the KL threshold search of the library == the numpy restatement,
+    on half-normal, exponential, spiky and empty histograms (512 bins keep the O(bins^2) numpy loop short)."""
+    from oracle.calibrator_ref import kl_threshold_bins as ref
+    from retinaface_b200.capi import kl_threshold_bins as lib
+    rng = np.random.default_rng(0)
+    cases = [np.histogram(np.abs(rng.normal(0, 1, 200_000)), bins=512, range=(0, 6))[0],
+             np.histogram(rng.exponential(1.0, 100_000), bins=512, range=(0, 20))[0],
+             np.histogram(np.concatenate([np.abs(rng.normal(0, 0.1, 50_000)), rng.uniform(5, 10, 50)]), bins=512, range=(0, 10))[0],
+             np.zeros(512, dtype=np.int64), np.r_[np.zeros(300), 5, np.zeros(211)].astype(np.int64)]
+    for h in cases:
+        a, b = lib(h.astype(np.uint32)), ref(h)
+        assert abs(a - b) <= 2, (a, b)          # identical up to summation-order ties between neighbouring candidates
+    assert 128 <= lib(cases[2].astype(np.uint32)) < 320     # most of the sparse uniform outliers in [5, 10) (bins >= 256) are clipped
+    assert lib(cases[0].astype(np.uint32)) > 300            # a half-normal keeps most of its range (no over-clipping)
