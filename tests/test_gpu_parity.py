@@ -443,10 +443,14 @@ def test_int8_calibrator_end_to_end(golden_image, tmp_path):
         eng = Engine(caffemodel(model), 448, 448, precision=RF_PREC_INT8, max_batch=2, int8_table=table)
         try:
             faces = eng.detect_batch([inp], 0.9, 0.4)[0]
-            gold = np.load(os.path.join(GOLDEN, f"dets_{model}_448x448.npz"))["faces_thr0.9"]
-            assert len(faces) == len(gold) == 5
-            for g in gold:
+            dets = np.load(os.path.join(GOLDEN, f"dets_{model}_448x448.npz"))
+            gold, gold_lo = dets["faces_thr0.9"], dets["faces_thr0.5"]
+            assert len(gold) == 5 and len(faces) >= 5
+            for g in gold:          # every FP32 face is found, boxes within 3 px, scores within 0.05
                 c = faces[np.argmin(np.abs(faces[:, 1:3] - g[1:3]).sum(1))]
                 assert np.abs(c[1:5] - g[1:5]).max() < 3.0 and abs(c[0] - g[0]) < 0.05, (model, c[:5], g[:5])
+            for c in faces:         # and nothing is invented: a face pushed over 0.9 by quantisation noise is an FP32 face at 0.5
+                g = gold_lo[np.argmin(np.abs(gold_lo[:, 1:3] - c[1:3]).sum(1))]
+                assert np.abs(c[1:5] - g[1:5]).max() < 3.0, (model, c[:5], g[:5])
         finally:
             eng.close()
