@@ -454,3 +454,39 @@ def test_int8_calibrator_end_to_end(golden_image, tmp_path):
                 assert np.abs(c[1:5] - g[1:5]).max() < 3.0, (model, c[:5], g[:5])
         finally:
             eng.close()
+
+
+@pytest.mark.parametrize("hw", [(416, 288), (320, 320), (96, 160)])
+def test_shipped_and_odd_network_sizes(hw, golden_image, post_oracle):
+    """The network sizes the reference's own prototxts carry (mnet25.prototxt:7 -> 416x288 (HxW),
+    mnet-deconv-0517.prototxt:7 -> 320x320) and a small non-square one: FP32 engine heads vs the numpy oracle
+    (2e-4), FP16 and INT8 tensor-core engines vs the FP32 engine's detections (same faces, 1.5 / 4 px)."""
+    from retinaface_b200 import RF_PREC_FP16, RF_PREC_FP32, RF_PREC_INT8, Engine
+    h, w = hw
+    model = "mnet-deconv-0517"
+    table = os.path.join(GOLDEN, "weights", model + ".table.int8")
+    inp = letterbox_bgr_u8(golden_image, h, w)
+    batch = np.stack([inp, np.roll(inp, 8, axis=1), inp[::-1].copy()])
+    e32 = Engine(caffemodel(model), h, w, precision=RF_PREC_FP32, max_batch=3)
+    try:
+        heads = e32.forward_heads(batch)
+        ref = MnetOracle(caffemodel(model)).forward(np.concatenate([preprocess_bgr_u8(b) for b in batch]))
+        for k, name in enumerate(topology.OUTPUT_BLOBS):
+            assert np.abs(heads[k] - ref[name]).max() < TOL_FP32, (hw, name)
+        base = e32.detect_batch(list(batch), 0.8, 0.4)
+    finally:
+        e32.close()
+    for prec, tol in ((RF_PREC_FP16, 1.5), (RF_PREC_INT8, 4.0)):
+        eng = Engine(caffemodel(model), h, w, precision=prec, max_batch=3, int8_table=table if prec == RF_PREC_INT8 else None)
+        try:
+            faces, idx = eng.detect_batch(list(batch), 0.8, 0.4, want_index=True)
+            hd = eng.forward_heads(batch)
+            for i in range(3):
+                _compare_dets(faces[i], idx[i], post_oracle.postprocess([x[i] for x in hd], h, w, 0.8, 0.4), f"{hw} prec={prec} img={i}")
+                strong = base[i][base[i][:, 0] > 0.95]           # faces well above the threshold must survive quantisation
+                for g in strong:
+                    assert len(faces[i]) > 0, (hw, prec, i)
+                    c = faces[i][np.argmin(np.abs(faces[i][:, 1:3] - g[1:3]).sum(1))]
+                    assert np.abs(c[1:5] - g[1:5]).max() < tol, (hw, prec, i, c[:5], g[:5])
+        finally:
+            eng.close()
