@@ -11,8 +11,10 @@ Printed JSON (rank 0, one line):
   value      faces/s, device-timed: inputs already resident in HBM (a ring of batches larger than
              2x L2 so that no step finds its input in L2), CUDA events on the library's stream,
              max over ranks, whole job (all GPUs).
-  e2e        the same metric through the public C-ABI call rf_detect_batch with HOST (pinned)
-             images: H2D + compute + D2H of the faces inside the timed region, every step.
+  e2e        the same metric through the public C ABI with HOST (pinned) images: every step copies its own
+             images H2D and reads its own faces back D2H inside the timed region -- rf_submit_batch /
+             rf_collect_batch with several batches in flight (throughput mode); `e2e.blocking` is the same
+             with one blocking rf_detect_batch per step (latency mode).
   roofline   dominant kernel: algorithmic bytes (layer-granular) / CUDA-event time of
              that kernel launched K times on the library's stream, vs MEASURED_PEAKS.json.
   cpu_baseline  the oracle (cv2.dnn FP32 forward of the same caffemodel through a generated prototxt +

@@ -14,6 +14,10 @@ Pieces (each function cites the reference file:line it restates):
                          ``model/mnet-deconv-0517.prototxt``) + a prototxt writer so that
                          ``cv2.dnn`` can execute it where /root/reference is absent.
 * ``mnet_numpy.py``   -- FP32 numpy restatement of the Caffe forward pass (9 head blobs).
+* ``mnet_int8.py``    -- integer oracle of the INT8 path: the exact quantisation scheme of RF_PREC_INT8 on the
+                         reference's calibration-table scales (TensorRT's own INT8 kernels are closed source).
+* ``calibrator_ref.py`` -- numpy restatement of the entropy-calibration threshold search of rf_calibrate_int8.
+* ``inputs.py``       -- the reference's OpenCV letter-box branch + the seeded synthetic inputs of SURVEY 8d.
 * ``postproc.c``      -- plain-C restatement of anchors / decode / clip / NMS
                          (``retinaface/RetinaFace.cpp:9-199,347-492,661-726``).
 * ``postproc.py``     -- ctypes loader for the C restatement and for ``oracle/_ref``.
