@@ -23,6 +23,7 @@
 #include "preprocess.cuh"
 #include "tc_conv.cuh"
 #include "tc_conv_i8.cuh"
+#include "stem_tc.cuh"
 
 using namespace rf;
 
@@ -365,7 +366,8 @@ void build_plan(rf_handle h) {
     bool stem_done = false;
     if constexpr (std::is_same<T, __half>::value) {
         if (h->use_tc) {
-            // conv0 + dw1 + pw2 fused on CUDA cores (kernels_simt.cuh k_stem)
+            // conv0 + dw1 + pw2 fused: the two dense layers on tensor cores (stem_tc.cuh), or all on CUDA cores
+            // (kernels_simt.cuh k_stem) with RF_FLAG_SIMT_STEM
             const FoldedConv &c0 = m.conv("mobilenet0_conv0_fwd"), &dw = m.conv("mobilenet0_conv1_fwd"), &pw = m.conv("mobilenet0_conv2_fwd");
             std::vector<float> w0(27 * 8), wd(72), wp(128);
             for (int o = 0; o < 8; o++)
@@ -377,17 +379,35 @@ void build_plan(rf_handle h) {
                 for (int c = 0; c < 8; c++) wp[c * 16 + o] = pw.w[(size_t)o * 8 + c];
             size_t ow0 = B.add_weights(w0), ob0 = B.add_weights(c0.b), owd = B.add_weights(wd), obd = B.add_weights(dw.b),
                    owp = B.add_weights(wp), obp = B.add_weights(pw.b);
+            // tensor-core operand images: B0 [4][16][8] (k = (tap*3 + c_bgr), n = out channel), B1 [2][16][8]
+            std::vector<__half> b0img(2 * 4 * 16 * 8, __float2half(0.f)), b1img(2 * 16 * 8, __float2half(0.f));
+            for (int k = 0; k < 27; k++)
+                for (int o = 0; o < 8; o++) {
+                    const float wv = w0[k * 8 + o];
+                    const __half hi = __float2half(wv);
+                    b0img[((k / 8) * 16 + o) * 8 + (k % 8)] = hi;                                            // w = hi + lo
+                    b0img[((4 + k / 8) * 16 + o) * 8 + (k % 8)] = __float2half(wv - __half2float(hi));
+                }
+            for (int c = 0; c < 8; c++)
+                for (int o = 0; o < 16; o++) b1img[(0 * 16 + o) * 8 + c] = __float2half(wp[c * 16 + o]);
+            size_t ob0img = B.add_weights_h(b0img), ob1img = B.add_weights_h(b1img);
+            const bool simt_stem = (h->cfg.flags & (RF_FLAG_SIMT_STEM | RF_FLAG_NO_TENSORCORE)) != 0;
             cur = B.tensor("mobilenet0_relu2_fwd", cur_h, cur_w, 16);
             int out = cur;
             Step s;
-            s.name = "stem_conv0+dw1+pw2_u8_to_16ch";
+            s.name = simt_stem ? "stem_conv0+dw1+pw2_u8_to_16ch" : "tc_stem_conv0+dw1+pw2_u8_to_16ch";
             s.out = {out};
             s.flops_per_img = 2.0 * cur_h * cur_w * (8 * 27 + 8 * 9 + 8 * 16);
             s.bytes_per_img = (double)H * W * 3 + (double)cur_h * cur_w * 16 * es;
             s.launch = [=](int n, cudaStream_t st) {
-                StemWeights sw{Wd(ow0), Wd(ob0), Wd(owd), Wd(obd), Wd(owp), Wd(obp)};
                 const int tiles = ((H / 2 + 15) / 16) * ((W / 2 + 15) / 16);
-                launch_k(k_stem<__half>, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), sw, n, H, W, 1.0f);
+                if (simt_stem) {
+                    StemWeights sw{Wd(ow0), Wd(ob0), Wd(owd), Wd(obd), Wd(owp), Wd(obp)};
+                    launch_k(k_stem<__half>, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), sw, n, H, W, 1.0f);
+                } else {
+                    StemTcArgs a{h->d_weights_h + ob0img, h->d_weights_h + ob1img, Wd(ob0), Wd(owd), Wd(obd), Wd(obp)};
+                    launch_k(k_stem_tc, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), a, n, H, W);
+                }
             };
             B.step(std::move(s));
             cur_c = 16;

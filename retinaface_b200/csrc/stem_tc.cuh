@@ -1,0 +1,244 @@
+// stem_tc.cuh -- the network stem on tensor cores (FP16 path): mobilenet0_conv0 (3x3 s2, 3->8) + BN + ReLU,
+// conv1 (depthwise 3x3) + BN + ReLU, conv2 (pointwise 8->16) + BN + ReLU  (prototxt:11-141) in one kernel,
+// u8 BGR image in, FP16 NHWC [n][H/2][W/2][16] out.
+//
+// The CUDA-core stem (kernels_simt.cuh k_stem) spends two thirds of its instructions on the 216 + 128 FMAs per
+// pixel of the two dense layers.  Here both become tcgen05 GEMMs with the accumulator in TMEM and only the
+// depthwise stencil stays on CUDA cores:
+//   per CTA: a 16x16 tile of the H/2 x W/2 map (256 threads)
+//   1. stage the 37x37x3 u8 input patch (32-bit loads)
+//   2. im2col of conv0 for the 18x18 ring (324 rows, padded to 3 x 128) straight into the UMMA A operand: each
+//      thread converts the 27 u8 taps of one position to FP16 (exact) -- K = 27 padded to 32
+//   3. 3 tiles x 2 x tcgen05.mma (M=128, N=16 (8 used), K=16): conv0 for the whole ring
+//   4. TMEM -> registers: + bias, ReLU, zero outside the map (= the depthwise conv's padding) -> shared (FP32)
+//   5. depthwise 3x3 + ReLU per output pixel on CUDA cores -> FP16 -> A operand of the pointwise GEMM
+//   6. 2 tiles x tcgen05.mma (M=128, N=16, K=16 (8 used)): conv2
+//   7. TMEM -> registers: + bias, ReLU, FP16 pack, 2 x 16-byte stores per pixel
+// conv0's folded weights are rounded to FP16 here (the CUDA-core stem keeps them FP32): relative 2^-11 per weight,
+// the same order as the FP16 rounding of every activation tensor downstream.
+#pragma once
+#include "tc_conv.cuh"
+
+namespace rf {
+
+struct StemTcArgs {
+    const __half *b0;       // conv0 B images: [hi, lo][4 groups][16 n][8] halfs, k = (ky*3+kx)*3 + c_bgr, n >= 8 and k >= 27
+                            // zero; w = hi + lo (two FP16 pieces, 22 significant bits) accumulated by two MMAs per K step
+    const __half *b1;       // conv2 B image: [2 groups][16 n][8] halfs, k = channel (k >= 8 zero)
+    const float *bias0;     // [8]
+    const float *wd, *bd;   // depthwise [9][8], [8]
+    const float *bias2;     // [16]
+};
+
+constexpr int STEM_LBO0 = 384 * 16 + 16;    // A0: 3 tiles x 128 rows
+constexpr int STEM_LBO1 = 256 * 16 + 16;    // A1: 2 tiles x 128 rows
+
+__global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict__ run, __half *__restrict__ out, StemTcArgs w,
+                                                    int n, int H, int W) {
+    __shared__ __align__(16) uint8_t s_in[37][116];
+    __shared__ __align__(128) unsigned char s_a0[4 * STEM_LBO0];
+    __shared__ __align__(128) __half s_b0[2 * 4 * 16 * 8];
+    __shared__ __align__(128) __half s_b1[2 * 16 * 8];
+    __shared__ __align__(16) float s_c0[18 * 18][8];
+    __shared__ __align__(16) float s_wd[9 * 8 + 8];
+    __shared__ float s_bias0[8], s_bias2[16];
+    __shared__ __align__(8) uint64_t bar0, bar1;
+    __shared__ uint32_t s_tmem;
+
+    unsigned char *s_a1 = s_a0;      // the pointwise operand reuses conv0's (dead once bar0 has completed)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int OH = H >> 1, OW = W >> 1;
+    const int tiles_x = (OW + 15) >> 4, tiles_y = (OH + 15) >> 4;
+    const int b = blockIdx.x / (tiles_x * tiles_y);
+    const int trem = blockIdx.x - b * tiles_x * tiles_y;
+    const int oy0 = (trem / tiles_x) << 4, ox0 = (trem % tiles_x) << 4;
+
+    if (tid == 0) {
+        tc::mbar_init(&bar0, 1);
+        tc::mbar_init(&bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tc::tmem_alloc<64>(&s_tmem);
+    pdl_trigger();
+    for (int i = tid; i < 2 * 4 * 16 * 8 / 8; i += 256) reinterpret_cast<uint4 *>(s_b0)[i] = reinterpret_cast<const uint4 *>(w.b0)[i];
+    if (tid >= 128 && tid < 128 + 2 * 16 * 8 / 8) reinterpret_cast<uint4 *>(s_b1)[tid - 128] = reinterpret_cast<const uint4 *>(w.b1)[tid - 128];
+    for (int i = tid; i < 9 * 8 + 8; i += 256) s_wd[i] = i < 72 ? w.wd[i] : w.bd[i - 72];
+    if (tid < 8) s_bias0[tid] = w.bias0[tid];
+    if (tid < 16) s_bias2[tid] = w.bias2[tid];
+    pdl_wait();
+    // ---- 1. stage the u8 patch (see k_stem) ------------------------------------------------------------------
+    const uint8_t *__restrict__ img = run->input + (size_t)b * H * W * 3;
+    const int iy0 = 2 * oy0 - 3, cb0 = (2 * ox0 - 3) * 3;
+    const int al0 = cb0 & ~3, mis = cb0 - al0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
+    const int rowbytes = W * 3;
+    {   // warp w stages rows w, w + 8, ...: lane = 32-bit word of the row; all loads in flight before the first store
+        uint32_t v[5];
+        const int gb = al0 + 4 * lane;
+        const bool fast = aligned && gb >= 0 && gb + 3 < rowbytes;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int r = warp + 8 * k, iy = iy0 + r;
+            v[k] = 0;
+            if (r < 37 && lane < 29 && iy >= 0 && iy < H) {
+                const uint8_t *rowp = img + (size_t)iy * rowbytes;
+                if (fast) {
+                    v[k] = __ldg(reinterpret_cast<const uint32_t *>(rowp + gb));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (gb + j >= 0 && gb + j < rowbytes) v[k] |= (uint32_t)rowp[gb + j] << (8 * j);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int r = warp + 8 * k;
+            if (r < 37 && lane < 29) *reinterpret_cast<uint32_t *>(&s_in[r][4 * lane]) = v[k];
+        }
+    }
+    __syncthreads();
+    // ---- 2. conv0 im2col -> A0 (rows = ring positions, K = (ky, kx, c) padded to 32) -----------------------------
+    for (int p = tid; p < 384; p += 256) {
+        uint32_t h2[16];                     // 32 halfs
+#pragma unroll
+        for (int i = 0; i < 16; i++) h2[i] = 0;
+        if (p < 324) {
+            const int py = p / 18, px = p - py * 18;
+            // 9 consecutive bytes per kernel row, starting at an arbitrary byte offset: three aligned words + funnel
+            // shifts; u8 -> FP16 without a convert: 0x6400 | b is the half 1024 + b, minus 1024 (exact)
+            const int off = mis + 6 * px, sh = (off & 3) * 8;
+            uint32_t bytes[3][3];
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(&s_in[2 * py + ky][off & ~3]);
+                const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];      // (off & 3) + 8 <= 11: three words cover the 9 bytes
+                bytes[ky][0] = __funnelshift_r(w0, w1, sh);
+                bytes[ky][1] = __funnelshift_r(w1, w2, sh);
+                bytes[ky][2] = __funnelshift_r(w2, 0u, sh);
+            }
+            const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
+#pragma unroll
+            for (int i = 0; i < 14; i++) {                  // K index k = ky * 9 + j; halfs (2i, 2i + 1) share a register
+                const int k0 = 2 * i, k1 = 2 * i + 1 < 27 ? 2 * i + 1 : 2 * i;
+                const int ra = k0 / 9, ja = k0 % 9, rb = k1 / 9, jb = k1 % 9;
+                const uint32_t wa = bytes[ra][ja >> 2], wb = bytes[rb][jb >> 2];
+                uint32_t biased;                            // (b_k0, 0x64, b_k1, 0x64)
+                if (ra == rb && (ja >> 2) == (jb >> 2))
+                    biased = __byte_perm(wa, 0x64646464u, (ja & 3) | 0x40 | ((jb & 3) << 8) | 0x4000);
+                else
+                    biased = __byte_perm(__byte_perm(wa, wb, (ja & 3) | ((4 + (jb & 3)) << 4)), 0x64646464u, 0x4140);
+                const __half2 r = __hsub2(*reinterpret_cast<const __half2 *>(&biased), k1024);
+                h2[i] = *reinterpret_cast<const uint32_t *>(&r);
+            }
+            h2[13] &= 0xffffu;                              // k = 27 is padding
+        }
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+            *reinterpret_cast<uint4 *>(s_a0 + g * STEM_LBO0 + p * 16) = make_uint4(h2[4 * g], h2[4 * g + 1], h2[4 * g + 2], h2[4 * g + 3]);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // ---- 3. conv0 GEMM ----------------------------------------------------------------------------------------------
+    if (tid == 0) {
+        const uint32_t a0 = tc::smem_u32(s_a0), b0 = tc::smem_u32(s_b0);
+        for (int t = 0; t < 3; t++)
+            for (int part = 0; part < 2; part++)
+                for (int ks = 0; ks < 2; ks++) {
+                    const uint64_t ad = tc::smem_desc(a0 + (uint32_t)(2 * ks) * STEM_LBO0 + (uint32_t)t * 128 * 16, STEM_LBO0, 128);
+                    const uint64_t bd = tc::smem_desc(b0 + (uint32_t)(part * 4 + 2 * ks) * 256, 256, 128);
+                    tc::mma_f16(tmem + (uint32_t)t * 16, ad, bd, idesc, (part | ks) ? 1u : 0u);
+                }
+        tc::mma_commit(&bar0);
+    }
+    tc::mbar_wait(&bar0, 0);
+    tc::tc_fence_after();
+    // ---- 4. conv0 epilogue -> s_c0 (FP32), zero outside the map ---------------------------------------------------------
+    for (int t = (warp >> 2); t < 3; t += 2) {
+        const int p = t * 128 + (warp & 3) * 32 + lane;
+        uint32_t r[16];
+        tc::tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)t * 16, r);
+        tc::tmem_ld_wait();
+        if (p < 324) {
+            const int py = p / 18, px = p - py * 18;
+            const int cy = oy0 - 1 + py, cx = ox0 - 1 + px;
+            const bool inside = cy >= 0 && cy < OH && cx >= 0 && cx < OW;
+            float v[8];
+#pragma unroll
+            for (int o = 0; o < 8; o++) v[o] = inside ? fmaxf(__uint_as_float(r[o]) + s_bias0[o], 0.f) : 0.f;
+            *reinterpret_cast<float4 *>(&s_c0[p][0]) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(&s_c0[p][4]) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    tc::tc_fence_before();           // conv0's TMEM columns are reused by the pointwise GEMM
+    __syncthreads();
+    // ---- 5. depthwise 3x3 + ReLU -> A1 (FP16, row = this thread's output pixel) -----------------------------------------
+    {
+        const int ty = tid >> 4, tx = tid & 15;
+        float d[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) d[c] = s_wd[72 + c];
+#pragma unroll 1
+        for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const float *src = &s_c0[(ty + ky) * 18 + tx + kx][0];
+                const float4 a0 = *reinterpret_cast<const float4 *>(src), a1 = *reinterpret_cast<const float4 *>(src + 4);
+                const float4 w0 = *reinterpret_cast<const float4 *>(&s_wd[(ky * 3 + kx) * 8]);
+                const float4 w1 = *reinterpret_cast<const float4 *>(&s_wd[(ky * 3 + kx) * 8 + 4]);
+                d[0] = fmaf(a0.x, w0.x, d[0]); d[1] = fmaf(a0.y, w0.y, d[1]); d[2] = fmaf(a0.z, w0.z, d[2]); d[3] = fmaf(a0.w, w0.w, d[3]);
+                d[4] = fmaf(a1.x, w1.x, d[4]); d[5] = fmaf(a1.y, w1.y, d[5]); d[6] = fmaf(a1.z, w1.z, d[6]); d[7] = fmaf(a1.w, w1.w, d[7]);
+            }
+#pragma unroll
+        for (int c = 0; c < 8; c++) d[c] = fmaxf(d[c], 0.f);
+        Vec8<__half> hv;
+        hv.from_float(d);
+        *reinterpret_cast<uint4 *>(s_a1 + tid * 16) = hv.v;
+        *reinterpret_cast<uint4 *>(s_a1 + STEM_LBO1 + tid * 16) = make_uint4(0, 0, 0, 0);      // K padding (channels 8..15)
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    // ---- 6. pointwise GEMM ----------------------------------------------------------------------------------------------
+    if (tid == 0) {
+        const uint32_t a1 = tc::smem_u32(s_a1), b1 = tc::smem_u32(s_b1);
+        for (int t = 0; t < 2; t++) {
+            const uint64_t ad = tc::smem_desc(a1 + (uint32_t)t * 128 * 16, STEM_LBO1, 128);
+            const uint64_t bd = tc::smem_desc(b1, 256, 128);
+            tc::mma_f16(tmem + (uint32_t)t * 16, ad, bd, idesc, 0u);
+        }
+        tc::mma_commit(&bar1);
+    }
+    tc::mbar_wait(&bar1, 0);
+    tc::tc_fence_after();
+    // ---- 7. epilogue: + bias, ReLU, FP16, store ----------------------------------------------------------------------------
+    {
+        const int t = warp >> 2;
+        const int row = t * 128 + (warp & 3) * 32 + lane;          // == the pixel's thread id of step 5
+        uint32_t r[16];
+        tc::tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)t * 16, r);
+        tc::tmem_ld_wait();
+        const int oy = oy0 + (row >> 4), ox = ox0 + (row & 15);
+        if (oy < OH && ox < OW) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] = fmaxf(__uint_as_float(r[j]) + s_bias2[j], 0.f);
+            Vec8<__half> v0, v1;
+            v0.from_float(f);
+            v1.from_float(f + 8);
+            __half *dst = out + (((size_t)b * OH + oy) * OW + ox) * 16;
+            v0.store(dst);
+            v1.store(dst + 8);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<64>(tmem);
+}
+
+}  // namespace rf

@@ -236,7 +236,8 @@ def test_fp16_forward_and_detect(model, golden_image, post_oracle):
 def test_fp16_tensor_core_layers_vs_oracle(golden_image):
     """tcgen05 path, layer by layer: every materialised activation of the FP16 engine against the FP32
     numpy oracle (relative to the tensor's max: 2e-2, FP16 storage through up to 30 layers), and against the
-    FP16 SIMT kernels (RF_FLAG_NO_TENSORCORE) which share the storage rounding (1.5e-2)."""
+    FP16 SIMT kernels (RF_FLAG_NO_TENSORCORE, which also selects the CUDA-core stem) that share the storage
+    rounding but not the FP16 operand rounding of the stem's pointwise GEMM (2e-2 as well)."""
     from retinaface_b200 import RF_PREC_FP16
     from retinaface_b200.capi import RF_FLAG_NO_TENSORCORE
     inp = letterbox_bgr_u8(golden_image, 448, 448)
@@ -263,9 +264,39 @@ def test_fp16_tensor_core_layers_vs_oracle(golden_image):
             e_ref = np.abs(a - ref[name]).max() / scale
             e_simt = np.abs(a - b).max() / scale
             assert e_ref < 2e-2, (name, "vs oracle", e_ref)
-            assert e_simt < 1.5e-2, (name, "vs simt fp16", e_simt)
+            assert e_simt < 2e-2, (name, "vs simt fp16", e_simt)
         for k in range(9):
             assert np.abs(h_tc[k] - h_simt[k]).max() < 2e-2, k
+    finally:
+        tc.close()
+        simt.close()
+
+
+@pytest.mark.parametrize("hw", [(448, 448), (96, 160), (416, 288)])
+def test_fp16_tensor_core_stem_vs_oracle(hw, golden_image):
+    """stem_tc.cuh (conv0 and conv2 as tcgen05 GEMMs, conv0 weights rounded to FP16) against the FP32 numpy
+    oracle and against the CUDA-core stem (RF_FLAG_SIMT_STEM, FP32 weights): mobilenet0_relu2_fwd within 2e-3 of
+    the tensor's max (FP16 storage of the output alone is 5e-4), including sizes whose 16x16 tiles are partial."""
+    from retinaface_b200 import RF_PREC_FP16
+    from retinaface_b200.capi import RF_FLAG_SIMT_STEM
+    h, w = hw
+    inp = letterbox_bgr_u8(golden_image, h, w)
+    batch = np.stack([inp, s_noise_batch(1, h, w, seed=3)[0], np.full_like(inp, 255)])
+    tc = _engine("mnet25", h, w, RF_PREC_FP16, max_batch=3)
+    simt = _engine("mnet25", h, w, RF_PREC_FP16, max_batch=3, flags=RF_FLAG_SIMT_STEM)
+    try:
+        tc.debug_keep_all()
+        simt.debug_keep_all()
+        tc.forward_heads(batch)
+        simt.forward_heads(batch)
+        name = "mobilenet0_relu2_fwd"
+        x = np.concatenate([preprocess_bgr_u8(b) for b in batch])
+        ref = MnetOracle(caffemodel("mnet25")).forward(x, want=[name])[name]
+        a, b = tc.debug_tensor(name, 3), simt.debug_tensor(name, 3)
+        scale = float(np.abs(ref).max())
+        assert np.abs(a - ref).max() / scale < 2e-3, np.abs(a - ref).max() / scale
+        assert np.abs(b - ref).max() / scale < 1e-3, np.abs(b - ref).max() / scale
+        assert np.abs(a - b).max() / scale < 2e-3
     finally:
         tc.close()
         simt.close()
