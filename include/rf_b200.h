@@ -148,6 +148,24 @@ int rf_postprocess(rf_handle h, const float *const heads[9], int n, float score_
                    float nms_threshold, rf_face *out_faces, int *out_counts, int32_t *out_anchor_index,
                    int *out_num_candidates);
 
+/* Test-time augmentation + map-back (the reference's `scales` parameter, RetinaFace.h:70, is unused and its
+ * map-back is commented out, RetinaFace.cpp:730-746).  One image, `nviews` views of it (1..RF_MAX_VIEWS, <= max_batch): view v
+ * is the image -- mirrored horizontally when views[v].flip -- letter-boxed into the top-left
+ * floor(net_w*shrink) x floor(net_h*shrink) corner of the network input (shrink in (0, 1]; 1 = the plain detect view).
+ * All views run as ONE batch; their detections are mapped back to ORIGINAL IMAGE pixels (x * scale_v, mirrored views
+ * un-mirrored with left/right landmarks swapped) and merged by one more greedy NMS (same rule and threshold as per view)
+ * across views, all on the GPU.  out_faces: [max_faces] in image coordinates; out_view_of (optional, [max_faces]): which view
+ * each kept face came from; out_view_scales (optional, [nviews]): the map-back factor of each view.
+ * views = {{1.0f, 0}} is detect + map-back. */
+typedef struct rf_view {
+    float shrink;
+    int32_t flip;
+} rf_view;
+#define RF_MAX_VIEWS 16
+int rf_detect_views(rf_handle h, const uint8_t *bgr, int width, int height, int row_stride, const rf_view *views, int nviews,
+                    float score_threshold, float nms_threshold, rf_face *out_faces, int *out_count, int32_t *out_view_of,
+                    float *out_view_scales);
+
 /* Preprocess parity: replaces imageROIResize8U3C + the OpenCV branch (RetinaFace.cpp:593-647):
  * letter-boxes one host image into a host net_h*net_w*3 u8 BGR buffer using the GPU kernel. */
 int rf_preprocess(rf_handle h, const uint8_t *bgr, int width, int height, int row_stride, uint8_t *out_net_sized);

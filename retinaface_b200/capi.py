@@ -21,7 +21,12 @@ EXPORTS = [
     "rf_pinned_input", "rf_device_input", "rf_detect_batch", "rf_submit_batch", "rf_collect_batch", "rf_detect_batch_device", "rf_forward_heads",
     "rf_postprocess", "rf_preprocess", "rf_get_net_size", "rf_num_anchors", "rf_stream", "rf_synchronize", "rf_fence", "rf_last_stream",
     "rf_launches_per_batch", "rf_profile_layers", "rf_debug_get_tensor", "rf_debug_keep_all", "rf_model_inspect", "rf_calibrate_int8", "rf_kl_threshold_bins",
+    "rf_detect_views",
 ]
+
+
+class _View(C.Structure):       # rf_view
+    _fields_ = [("shrink", C.c_float), ("flip", C.c_int32)]
 
 
 class RfError(RuntimeError):
@@ -75,6 +80,8 @@ def load_library() -> C.CDLL:
     lib.rf_get_net_size.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
     lib.rf_detect_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rf_detect_views.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(_View), C.c_int, C.c_float, C.c_float,
+                                    C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
     lib.rf_submit_batch.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_float, C.POINTER(C.c_int)]
     lib.rf_collect_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.rf_detect_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
@@ -272,6 +279,21 @@ class Engine:
         out = np.empty((self.net_h, self.net_w, 3), dtype=np.uint8)
         self._check(self.lib.rf_preprocess(self.h, img.ctypes.data, img.shape[1], img.shape[0], 0, out.ctypes.data))
         return out
+
+    def detect_views(self, img: np.ndarray, views, thr: float, nms: float):
+        """rf_detect_views: one image, views = [(shrink, flip), ...] run as one batch, merged on the GPU.  Returns
+        (faces [k, 15] in ORIGINAL IMAGE pixels, view index of each face [k], map-back scale of each view)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        nv = len(views)
+        varr = (_View * max(nv, 1))(*[_View(float(s), int(bool(f))) for s, f in views])
+        faces = np.empty((self.max_faces, 15), dtype=np.float32)
+        view_of = np.empty(self.max_faces, dtype=np.int32)
+        scales = np.empty(max(nv, 1), dtype=np.float32)
+        count = C.c_int(0)
+        self._check(self.lib.rf_detect_views(self.h, C.c_void_p(img.ctypes.data), img.shape[1], img.shape[0], 0, varr, nv, C.c_float(thr),
+                                             C.c_float(nms), C.c_void_p(faces.ctypes.data), C.byref(count),
+                                             C.c_void_p(view_of.ctypes.data), C.c_void_p(scales.ctypes.data)))
+        return faces[:count.value].copy(), view_of[:count.value].copy(), scales[:nv].copy()
 
     def calibrate_int8(self, images: np.ndarray, out_table: str):
         """INT8 entropy calibration on an RF_PREC_FP32 engine; writes a TensorRT-format table."""

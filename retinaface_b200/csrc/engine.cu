@@ -100,6 +100,7 @@ struct rf_handle_s {
     // io
     uint8_t *d_input = nullptr;       // [max_batch][H][W][3] u8 BGR
     uint8_t *h_input = nullptr;       // pinned mirror
+    PostBuffers pb_merge{};           // rf_detect_views: candidates of all views of one image (lazily allocated)
     uint8_t *d_raw = nullptr;         // one raw caller image (max_image) for the letterbox kernel
     uint8_t *h_raw = nullptr;         // pinned
     size_t raw_bytes = 0;
@@ -343,7 +344,7 @@ DwGeom dw_geometry(int C, int N, int IH, int IW, int S) {
             }
             R |= 1;
             TcDwArgs a{};
-            a.C = C; a.Rmax = R; a.Kpad = Kpad; a.N = N / nsplit;
+            a.C = C; a.Rmax = R; a.Kpad = Kpad; a.N = N / nsplit; a.rows = rows;
             if (R <= TC_MAX_R && tc_dw_smem_bytes(a) <= (size_t)TC_SMEM_LIMIT) return {rows, nsplit, R};
         }
     }
@@ -808,7 +809,7 @@ DwGeom dw_geometry_i8(int C, int N, int IH, int IW, int S) {
             }
             R |= 1;
             TcDwArgsI8 a{};
-            a.C = C; a.Rmax = R; a.Kpad = Kpad; a.N = N / nsplit;
+            a.C = C; a.Rmax = R; a.Kpad = Kpad; a.N = N / nsplit; a.rows = rows;
             if (R <= TC_MAX_R && tc_dw_i8_smem_bytes(a) <= (size_t)TC_SMEM_LIMIT) return {rows, nsplit, R};
         }
     }
@@ -1180,6 +1181,8 @@ void destroy(rf_handle h) {
         if (h->fence) cudaEventDestroy(h->fence);
         if (h->stream) cudaStreamDestroy(h->stream);
     }
+    cudaFree(h->pb_merge.cand_keys); cudaFree(h->pb_merge.cand_recs); cudaFree(h->pb_merge.cand_count); cudaFree(h->pb_merge.sort_scratch);
+    cudaFree(h->pb_merge.flag_scratch); cudaFree(h->pb_merge.out_dets); cudaFree(h->pb_merge.out_counts); cudaFree(h->pb_merge.out_total_kept);
     cudaFree(h->d_weights); cudaFree(h->d_weights_h); cudaFree(h->d_weights_q); cudaFree(h->d_input); cudaFree(h->d_raw);
     for (auto p : h->d_blobs) cudaFree(p);
     cudaFreeHost(h->h_input); cudaFreeHost(h->h_raw); cudaFreeHost(h->h_dets); cudaFreeHost(h->h_counts);
@@ -1596,6 +1599,70 @@ int rf_collect_batch(rf_handle h, int ticket, rf_face *out_faces, int *out_count
     }
     sl.busy = false;
     h->collect_seq++;
+    return RF_OK;
+}
+
+static void ensure_merge_buffers(rf_handle h) {
+    PostBuffers &pb = h->pb_merge;
+    if (pb.cand_keys) return;
+    const int A = h->cfg.max_batch * h->cfg.max_faces;       // every view may contribute max_faces candidates
+    int ap2 = 1;
+    while (ap2 < A) ap2 <<= 1;
+    pb.anchors_per_image = A; pb.anchors_pow2 = ap2; pb.max_faces = h->cfg.max_faces;
+    CK(cudaMalloc(&pb.cand_keys, sizeof(unsigned long long) * (size_t)A));
+    CK(cudaMalloc(&pb.cand_recs, sizeof(rf_det) * (size_t)A));
+    CK(cudaMalloc(&pb.cand_count, sizeof(int)));
+    CK(cudaMemset(pb.cand_count, 0, sizeof(int)));
+    CK(cudaMalloc(&pb.sort_scratch, sizeof(unsigned long long) * (size_t)ap2));
+    CK(cudaMalloc(&pb.flag_scratch, (size_t)ap2));
+    CK(cudaMalloc(&pb.out_dets, sizeof(rf_det) * (size_t)pb.max_faces));
+    CK(cudaMalloc(&pb.out_counts, sizeof(int)));
+    CK(cudaMalloc(&pb.out_total_kept, sizeof(int)));
+    CK(cudaMemset(pb.out_counts, 0, sizeof(int)));
+}
+
+int rf_detect_views(rf_handle h, const uint8_t *bgr, int width, int height, int row_stride, const rf_view *views, int nviews, float thr,
+                    float nms, rf_face *out_faces, int *out_count, int32_t *out_view_of, float *out_view_scales) {
+    if (!h || !bgr || !views || !out_count || width <= 0 || height <= 0) return fail(h, RF_ERR_INVALID_ARG, "rf_detect_views: bad arguments");
+    if (nviews < 1 || nviews > RF_MAX_VIEWS || nviews > h->cfg.max_batch)
+        return fail(h, RF_ERR_CAPACITY, fmt("rf_detect_views: %d views, limit min(RF_MAX_VIEWS = %d, max_batch = %d)", nviews, RF_MAX_VIEWS, h->cfg.max_batch));
+    if (width > h->cfg.max_image_w || height > h->cfg.max_image_h) return fail(h, RF_ERR_CAPACITY, "rf_detect_views: image larger than max_image");
+    for (int v = 0; v < nviews; v++)
+        if (!(views[v].shrink > 0.f && views[v].shrink <= 1.f)) return fail(h, RF_ERR_INVALID_ARG, fmt("rf_detect_views: view %d: shrink must be in (0, 1]", v));
+    static_assert(RF_MAX_VIEWS == RF_MAX_VIEWS_DEV, "view capacity of the merge kernel");
+    const int Hn = h->cfg.net_h, Wn = h->cfg.net_w, mf = h->cfg.max_faces;
+    const size_t img_bytes = (size_t)Hn * Wn * 3;
+    const int rs = row_stride ? row_stride : width * 3;
+    try {
+        CK(cudaSetDevice(h->device));
+        switch_ctx(h, 0);
+        ensure_merge_buffers(h);
+        CK(cudaStreamSynchronize(h->stream));          // h_raw is single-buffered
+        for (int y = 0; y < height; y++) memcpy(h->h_raw + (size_t)y * width * 3, bgr + (size_t)y * rs, (size_t)width * 3);
+        CK(cudaMemcpyAsync(h->d_raw, h->h_raw, (size_t)width * height * 3, cudaMemcpyHostToDevice, h->stream));
+        ViewSet vs{};
+        vs.nviews = nviews;
+        vs.img_w_minus1 = (float)(width - 1);
+        for (int v = 0; v < nviews; v++) {
+            const int bw = std::max(1, (int)(Wn * views[v].shrink)), bh = std::max(1, (int)(Hn * views[v].shrink));
+            vs.flip[v] = views[v].flip ? 1 : 0;
+            vs.scale[v] = launch_letterbox_view(h->d_raw, width, height, h->d_input + (size_t)v * img_bytes, Wn, Hn, bw, bh, vs.flip[v], h->stream);
+            if (out_view_scales) out_view_scales[v] = vs.scale[v];
+        }
+        set_params(h, thr, nms);
+        forward_graph(h, nviews);
+        launch_merge_views(h->pb, vs, h->pb_merge, h->stream);
+        launch_nms(1, h->d_params, h->pb_merge, h->stream);
+        CK(cudaMemcpyAsync(h->h_counts, h->pb_merge.out_counts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_dets, h->pb_merge.out_dets, sizeof(rf_det) * (size_t)mf, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const int k = h->h_counts[0];
+        *out_count = k;
+        for (int j = 0; j < k; j++) {
+            if (out_faces) out_faces[j] = h->h_dets[j].face;
+            if (out_view_of) out_view_of[j] = h->h_dets[j].anchor_index / mf;
+        }
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
     return RF_OK;
 }
 

@@ -320,6 +320,35 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms(const PostParams *__restric
     }
 }
 
+
+// ---- test-time augmentation: views -> one candidate list in image coordinates (postproc.cuh) -------------------------
+__global__ void __launch_bounds__(256) k_merge_views(PostBuffers src, ViewSet vs, PostBuffers dst) {
+    const int v = blockIdx.x;
+    const int n = min(src.out_counts[v], src.max_faces);
+    const float sc = vs.scale[v], wm1 = vs.img_w_minus1;
+    const bool flip = vs.flip[v] != 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const rf_face f = src.out_dets[(size_t)v * src.max_faces + j].face;
+        rf_det d;
+        d.face.score = f.score;
+        const float x1 = __fmul_rn(f.x1, sc), x2 = __fmul_rn(f.x2, sc);          // RetinaFace.cpp:733-734: rect.x1 * scale ...
+        d.face.y1 = __fmul_rn(f.y1, sc);
+        d.face.y2 = __fmul_rn(f.y2, sc);
+        d.face.x1 = flip ? __fsub_rn(wm1, x2) : x1;
+        d.face.x2 = flip ? __fsub_rn(wm1, x1) : x2;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            // mirrored view: the detector's "left eye" is the subject's right one -- swap 0<->1 and 3<->4 (2 = nose)
+            const int ks = flip ? (k == 0 ? 1 : k == 1 ? 0 : k == 3 ? 4 : k == 4 ? 3 : 2) : k;
+            const float x = __fmul_rn(f.lx[ks], sc);                                // :739
+            d.face.lx[k] = flip ? __fsub_rn(wm1, x) : x;
+            d.face.ly[k] = __fmul_rn(f.ly[ks], sc);
+        }
+        d.anchor_index = v * src.max_faces + j;
+        append_candidate(dst, 0, d);
+    }
+}
+
 size_t nms_smem_bytes(int max_faces) { return sizeof(int) * (size_t)max_faces; }
 
 }  // namespace
@@ -362,6 +391,11 @@ void launch_blob_decode(const float *const blobs[9], const LevelDesc lv[3], int 
 
 void launch_nms(int n, const PostParams *params, const PostBuffers &pb, cudaStream_t s) {
     launch_k(k_nms, dim3(n), dim3(NMS_THREADS), nms_smem_bytes(pb.max_faces), s, params, pb);
+}
+
+void launch_merge_views(const PostBuffers &src, const ViewSet &vs, const PostBuffers &dst, cudaStream_t s) {
+    // dst.cand_count[0] is zero here: cleared at allocation and by every k_nms on dst (self-cleaning)
+    k_merge_views<<<vs.nviews, 256, 0, s>>>(src, vs, dst);
 }
 
 cudaError_t postproc_init() {

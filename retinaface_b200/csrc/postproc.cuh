@@ -41,6 +41,20 @@ void launch_blob_decode(const float *const blobs[9], const LevelDesc lv[3], int 
 // Sort candidates by (score desc, emission index asc) and run greedy NMS; one CTA per image.
 void launch_nms(int n, const PostParams *params, const PostBuffers &pb, cudaStream_t s);
 
+// Test-time augmentation: gather the kept detections of `nviews` views (src.out_dets / out_counts, network
+// coordinates of each view) into ONE candidate list in original-image coordinates: x *= scale[v] (the reference's map-back,
+// RetinaFace.cpp:732-738), mirrored views are un-mirrored (x -> img_w-1 - x, box corners and left/right landmarks swapped).
+// Candidate id (rf_det::anchor_index of the merged records) = view * max_faces + rank in the view.  launch_nms(1, ..., dst)
+// then selects across views.
+constexpr int RF_MAX_VIEWS_DEV = 16;
+struct ViewSet {
+    int nviews;
+    float img_w_minus1;
+    float scale[RF_MAX_VIEWS_DEV];
+    int flip[RF_MAX_VIEWS_DEV];
+};
+void launch_merge_views(const PostBuffers &src, const ViewSet &vs, const PostBuffers &dst, cudaStream_t s);
+
 // dynamic shared memory the NMS kernel wants (set once at init)
 cudaError_t postproc_init();
 

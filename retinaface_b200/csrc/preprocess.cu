@@ -49,18 +49,22 @@ __device__ __forceinline__ Tap tap_of(int d, int sn, double scale) {
 
 __global__ void __launch_bounds__(256) k_letterbox(const uint8_t *__restrict__ src, int sw, int sh,
                                                    uint8_t *__restrict__ dst, int net_w, int net_h, int dw, int dh,
-                                                   double scale, int identity) {
+                                                   double scale, int identity, int flip) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= net_w) return;
     uint8_t *o = dst + ((size_t)y * net_w + x) * 3;
     if (x >= dw || y >= dh) { o[0] = 0; o[1] = 0; o[2] = 0; return; }
+    // flip: the view is the letter-box of the horizontally mirrored image -- every source column index is mirrored, the
+    // taps are those of the mirrored image (== cv::resize(cv::flip(img, 1)) bit for bit)
     if (identity) {
-        const uint8_t *p = src + ((size_t)y * sw + x) * 3;
+        const uint8_t *p = src + ((size_t)y * sw + (flip ? sw - 1 - x : x)) * 3;
         o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
         return;
     }
-    const Tap tx = tap_of<true>(x, sw, scale), ty = tap_of<false>(y, sh, scale);
+    Tap tx = tap_of<true>(x, sw, scale);
+    const Tap ty = tap_of<false>(y, sh, scale);
+    if (flip) { tx.s0 = sw - 1 - tx.s0; tx.s1 = sw - 1 - tx.s1; }
     const uint8_t *r0 = src + (size_t)ty.s0 * sw * 3, *r1 = src + (size_t)ty.s1 * sw * 3;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -74,11 +78,20 @@ __global__ void __launch_bounds__(256) k_letterbox(const uint8_t *__restrict__ s
 }  // namespace
 
 void launch_letterbox(const uint8_t *src, int w, int h, uint8_t *dst, int net_w, int net_h, cudaStream_t s) {
+    launch_letterbox_view(src, w, h, dst, net_w, net_h, net_w, net_h, 0, s);
+}
+
+float launch_letterbox_view(const uint8_t *src, int w, int h, uint8_t *dst, int net_w, int net_h, int box_w, int box_h, int flip,
+                            cudaStream_t s) {
     int dw, dh;
     double scale;
-    letterbox_geometry(w, h, net_w, net_h, &dw, &dh, &scale);
+    letterbox_geometry(w, h, box_w, box_h, &dw, &dh, &scale);
     dim3 grid((net_w + 255) / 256, net_h);
-    k_letterbox<<<grid, 256, 0, s>>>(src, w, h, dst, net_w, net_h, dw, dh, scale, scale == 1.0 ? 1 : 0);
+    k_letterbox<<<grid, 256, 0, s>>>(src, w, h, dst, net_w, net_h, dw, dh, scale, scale == 1.0 ? 1 : 0, flip);
+    // the reference's own float `scale` (RetinaFace.cpp:587-591), the factor its map-back multiplies by (:732-738)
+    const float sw = (float)(1.0 * w / box_w), sh = (float)(1.0 * h / box_h);
+    const float sc = sw > sh ? sw : sh;
+    return sc > 1.0f ? sc : 1.0f;
 }
 
 }  // namespace rf

@@ -22,6 +22,12 @@ namespace rf {
 // shrink by max(w/net_w, h/net_h, 1) (never up-scales), anchor top-left, zero the rest.
 void launch_letterbox(const uint8_t *src, int w, int h, uint8_t *dst, int net_w, int net_h, cudaStream_t s);
 
+// One view of a test-time-augmentation set: the image, optionally mirrored horizontally, fitted into the
+// top-left box_w x box_h corner of the network input (box <= net: a smaller box is a smaller test scale), zero elsewhere.
+// Returns the reference's map-back factor for this view (RetinaFace.cpp:587-591,732-738).
+float launch_letterbox_view(const uint8_t *src, int w, int h, uint8_t *dst, int net_w, int net_h, int box_w, int box_h, int flip,
+                            cudaStream_t s);
+
 // Host helper: output size + scale the way RetinaFace::detect + cv::resize compute them.
 void letterbox_geometry(int w, int h, int net_w, int net_h, int *dw, int *dh, double *inv_scale);
 

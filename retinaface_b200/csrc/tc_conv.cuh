@@ -185,7 +185,9 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem, int N, const float *s
 }
 
 inline size_t tc_conv_smem_bytes(const TcConvArgs &a) {
-    return (size_t)(a.Cin / 8) * a.R * 16 + (size_t)a.taps * a.Cin * a.N * 2 + (a.up ? (size_t)(a.Cin / 8) * a.Cmax * 16 : 0) + 128;
+    // staged range + weight image (+ UPADD: staged coarse rows) + the position tables (s_off, UPADD: s_yx)
+    return (size_t)(a.Cin / 8) * a.R * 16 + (size_t)a.taps * a.Cin * a.N * 2 + (a.up ? (size_t)(a.Cin / 8) * a.Cmax * 16 : 0) +
+           (size_t)a.R * 4 * (a.up ? 2 : 1) + 128;
 }
 
 template <int NT, bool UPADD>
@@ -193,11 +195,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_b, bar_done;
     __shared__ uint32_t s_tmem;
-    __shared__ int s_off[TC_MAX_R];      // staged position -> element offset of its pixel in `in`, -1 = zero padding
     __shared__ float s_bias[256];
     __shared__ __align__(16) __half s_uw[UPADD ? 64 * 16 : 8];   // [tap][channel] deconv weights as FP16 (bilinear taps are exact)
     __shared__ int s_crow[2];            // UPADD: [lo, hi] global coarse rows (b*UH + i) the tile reads
-    __shared__ int s_yx[UPADD ? TC_MAX_R : 1];   // UPADD: staged position -> (global fine row b*H+y) << 12 | x
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int pad = a.taps == 9 ? 1 : 0;
@@ -205,8 +205,13 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     const uint32_t lbo_s = (uint32_t)a.R * 16;
     unsigned char *sS = smem;
     unsigned char *sB = smem + (size_t)G * lbo_s;
-    const long m0 = (long)blockIdx.x * 128;
-    const long lo = m0 - (long)(a.Wp + 1) * pad;
+    // position tables behind the operands (sized by R, so that the footprint -- and with it the number of co-resident
+    // CTAs -- follows the layer): s_off: staged position -> element offset of its pixel in `in`, -1 = zero padding;
+    // UPADD: s_yx: staged position -> (global fine row b*H+y) << 12 | x
+    int *s_off = reinterpret_cast<int *>(sB + (size_t)a.taps * a.Cin * a.N * 2 + (UPADD ? (size_t)G * a.Cmax * 16 : 0));
+    int *s_yx = s_off + a.R;
+    const int m0 = blockIdx.x * 128;
+    const int lo = m0 - (a.Wp + 1) * pad;
 
     if (tid == 0) {
         s_crow[0] = 0x7fffffff; s_crow[1] = -1;
@@ -224,14 +229,14 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     // position table, one warp per padded row (no per-position divisions): p = prow * Wp + xx
     {
         const int lane = tid & 31;
-        const long prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;          // floor
-        const long prow1 = (lo + a.R - 1) / a.Wp;
-        for (long prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
+        const int prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;          // floor
+        const int prow1 = (lo + a.R - 1) / a.Wp;
+        for (int prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
             const int b = prow >= 0 ? (int)(prow / a.Hp) : -1;
-            const int yy = prow >= 0 ? (int)(prow - (long)b * a.Hp) : 0;
+            const int yy = prow >= 0 ? (int)(prow - b * a.Hp) : 0;
             const bool rowok = prow >= 0 && b < a.nimg && yy < a.H;
             for (int xx = lane; xx < a.Wp; xx += 32) {
-                const long pl = prow * a.Wp + xx - lo;
+                const int pl = prow * a.Wp + xx - lo;
                 if (pl < 0 || pl >= a.R) continue;
                 int off = -1;
                 if (rowok && xx >= pad && xx < a.W + pad) {
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     {
         const int r = (warp & 3) * 32 + (tid & 31);
         const int off = s_off[(int)(m0 - lo) + r];               // element offset / Cin == output pixel index
-        tc_epilogue(tmem, a.N, s_bias, a.out, off >= 0 ? (long)(off / a.Cin) : -1, 0);
+        tc_epilogue(tmem, a.N, s_bias, a.out, off >= 0 ? (off / a.Cin) : -1, 0);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -370,8 +375,13 @@ struct TcDwArgs {
     __half *out;            // [nimg][OH][OW][Ntotal]
 };
 
+// A operand of the pointwise GEMM: [Kpad/8 groups][rows][16 B], group stride rows*16 + 16.  The UMMA tile is M = 128:
+// with rows = 64 the instruction reads 64 more rows per group (the next group's / 1 KB of slack behind the last one) whose
+// results are never read back.
+__host__ __device__ inline uint32_t tc_dw_lbo_a(int rows) { return (uint32_t)rows * 16 + 16; }
 inline size_t tc_dw_smem_bytes(const TcDwArgs &a) {
-    return (size_t)((a.C + 7) / 8) * a.Rmax * 16 + (size_t)(a.Kpad / 8) * TC_LBO_A + (size_t)a.Kpad * a.N * 2 + 128;
+    return (size_t)((a.C + 7) / 8) * a.Rmax * 16 + (size_t)(a.Kpad / 8) * tc_dw_lbo_a(a.rows) + (size_t)(128 - a.rows) * 16 +
+           (size_t)a.Kpad * a.N * 2 + (size_t)a.Rmax * 4 + 128;
 }
 
 // WREG: depthwise weights in registers (C >= 64: few threads share a channel group) or in shared memory
@@ -382,7 +392,6 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 3) k_tc_dwpw_staged(con
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_b, bar_done;
     __shared__ uint32_t s_tmem;
-    __shared__ int s_off[TC_MAX_R];
     __shared__ int s_cpos[128];          // GEMM row -> staged index of its stencil centre, -1 = no output
     __shared__ float s_bias[256];
     __shared__ __align__(16) float s_dw[WREG ? 4 : 10 * 64];   // !WREG: [tap][C] weights, [9] = bias (C <= 64)
@@ -394,15 +403,17 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 3) k_tc_dwpw_staged(con
     const uint32_t lbo_s = (uint32_t)a.Rmax * 16;
     unsigned char *sS = smem;
     unsigned char *sA = smem + (size_t)G * lbo_s;
-    unsigned char *sB = sA + (size_t)(a.Kpad / 8) * TC_LBO_A;
-    const long M = (long)a.nimg * a.OH * a.OW;
-    const long m0 = (long)blockIdx.x * a.rows;
-    const long mlast = min(m0 + a.rows, M) - 1;
-    auto centre = [&](long m) -> long {
-        const int ox = (int)(m % a.OW), oy = (int)((m / a.OW) % a.OH), b = (int)(m / ((long)a.OW * a.OH));
-        return ((long)b * a.Hp + (long)oy * a.S) * a.Wp + (long)ox * a.S + 1;
+    const uint32_t lbo_a = tc_dw_lbo_a(a.rows);
+    unsigned char *sB = sA + (size_t)(a.Kpad / 8) * lbo_a + (size_t)(128 - a.rows) * 16;
+    int *s_off = reinterpret_cast<int *>(sB + (size_t)a.Kpad * a.N * 2);      // staged position -> element offset, -1 = padding
+    const int M = a.nimg * a.OH * a.OW;
+    const int m0 = blockIdx.x * a.rows;
+    const int mlast = min(m0 + a.rows, M) - 1;
+    auto centre = [&](int m) -> int {
+        const int ox = (int)(m % a.OW), oy = (int)((m / a.OW) % a.OH), b = (int)(m / (a.OW * a.OH));
+        return (b * a.Hp + oy * a.S) * a.Wp + ox * a.S + 1;
     };
-    const long lo = centre(m0) - a.Wp - 1;
+    const int lo = centre(m0) - a.Wp - 1;
     const int R = (int)(centre(mlast) + a.Wp + 1 - lo) + 1;
     if (R > a.Rmax) __trap();            // host-side geometry (engine.cu dw_geometry) must bound every tile
 
@@ -431,21 +442,21 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 3) k_tc_dwpw_staged(con
     }
     {
         const int lane = tid & 31;
-        const long prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;          // floor
-        const long prow1 = (lo + R - 1) / a.Wp;
-        for (long prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
+        const int prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;          // floor
+        const int prow1 = (lo + R - 1) / a.Wp;
+        for (int prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
             const int b = prow >= 0 ? (int)(prow / a.Hp) : -1;
-            const int yy = prow >= 0 ? (int)(prow - (long)b * a.Hp) : 0;
+            const int yy = prow >= 0 ? (int)(prow - b * a.Hp) : 0;
             const bool rowok = prow >= 0 && b < a.nimg && yy < a.IH;
             for (int xx = lane; xx < a.Wp; xx += 32) {
-                const long pl = prow * a.Wp + xx - lo;
+                const int pl = prow * a.Wp + xx - lo;
                 if (pl < 0 || pl >= R) continue;
                 s_off[pl] = (rowok && xx >= 1 && xx <= a.IW) ? ((b * a.IH + yy) * a.IW + (xx - 1)) * a.C : -1;
             }
         }
     }
     if (tid < 128) {
-        const long m = m0 + tid;
+        const int m = m0 + tid;
         s_cpos[tid] = (tid < a.rows && m < M) ? (int)(centre(m) - lo) : -1;
     }
     __syncthreads();
@@ -494,11 +505,11 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 3) k_tc_dwpw_staged(con
             for (int i = 0; i < 8; i++) acc[i] = fmaxf(acc[i], 0.f);
             Vec8<__half> o;
             o.from_float(acc);
-            *reinterpret_cast<uint4 *>(sA + (size_t)g_own * TC_LBO_A + (size_t)r * 16) = o.v;
+            *reinterpret_cast<uint4 *>(sA + (size_t)g_own * lbo_a + (size_t)r * 16) = o.v;
         }
     } else {                                  // K padding group of the Cin = 8 layer: zeros
         for (int r = tid / GA; r < a.rows; r += TC_THREADS / GA)
-            *reinterpret_cast<uint4 *>(sA + (size_t)g_own * TC_LBO_A + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(sA + (size_t)g_own * lbo_a + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
@@ -512,7 +523,7 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 3) k_tc_dwpw_staged(con
         const uint32_t a_addr = tc::smem_u32(sA), b_addr = tc::smem_u32(sB);
         const uint32_t lbo_b = (uint32_t)a.N * 16;
         for (int ks = 0; ks < (a.Kpad >> 4); ks++) {
-            const uint64_t ad = tc::smem_desc(a_addr + (uint32_t)(2 * ks) * TC_LBO_A, TC_LBO_A, 128);
+            const uint64_t ad = tc::smem_desc(a_addr + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
             const uint64_t bd = tc::smem_desc(b_addr + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
             tc::mma_f16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
         }
@@ -522,7 +533,7 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 3) k_tc_dwpw_staged(con
     tc::tc_fence_after();
     {
         const int r = (warp & 3) * 32 + (tid & 31);
-        const long m = m0 + r;
+        const int m = m0 + r;
         TcOut o{a.out, a.Ntotal, a.Ntotal, 1, nullptr, 0, 0};
         tc_epilogue(tmem, a.N, s_bias, o, (r < a.rows && m < M) ? m : -1, (int)blockIdx.y * a.N);
     }

@@ -103,7 +103,8 @@ struct TcConvArgsI8 {
 inline int tc_i8_gs(int Cin) { int g = Cin / 16; return g < 2 ? 2 : g; }
 inline size_t tc_conv_i8_smem_bytes(const TcConvArgsI8 &a) {
     const int GS = tc_i8_gs(a.Cin);
-    return (size_t)GS * a.R * 16 + (size_t)a.taps * GS * 16 * a.N + (a.up ? (size_t)(a.Cin / 16) * a.Cmax * 16 : 0) + 128;
+    return (size_t)GS * a.R * 16 + (size_t)a.taps * GS * 16 * a.N + (a.up ? (size_t)(a.Cin / 16) * a.Cmax * 16 : 0) +
+           (size_t)a.R * 4 * (a.up ? 2 : 1) + 128;      // + position tables (s_pix, UPADD: s_yx)
 }
 
 template <int NT, bool UPADD>
@@ -111,11 +112,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged_i8(const TcConvAr
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_b, bar_done;
     __shared__ uint32_t s_tmem;
-    __shared__ int s_pix[TC_MAX_R];      // staged position -> pixel index in `in`, -1 = zero padding
     __shared__ float s_mult[256], s_bq[256];
     __shared__ __align__(16) float s_uw[UPADD ? 64 * 16 : 4];   // [tap][channel]
     __shared__ int s_crow[2];
-    __shared__ int s_yx[UPADD ? TC_MAX_R : 1];
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int pad = a.taps == 9 ? 1 : 0;
@@ -124,8 +123,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged_i8(const TcConvAr
     const uint32_t lbo_s = (uint32_t)a.R * 16;
     unsigned char *sS = smem;
     unsigned char *sB = smem + (size_t)GS * lbo_s;
-    const long m0 = (long)blockIdx.x * 128;
-    const long lo = m0 - (long)(a.Wp + 1) * pad;
+    // position tables behind the operands: s_pix: staged position -> pixel index in `in`, -1 = zero padding; UPADD: s_yx
+    int *s_pix = reinterpret_cast<int *>(sB + (size_t)a.taps * GS * 16 * a.N + (UPADD ? (size_t)G * a.Cmax * 16 : 0));
+    int *s_yx = s_pix + a.R;
+    const int m0 = blockIdx.x * 128;
+    const int lo = m0 - (a.Wp + 1) * pad;
 
     if (tid == 0) {
         s_crow[0] = 0x7fffffff; s_crow[1] = -1;
@@ -142,14 +144,14 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged_i8(const TcConvAr
     if (UPADD) for (int i = tid; i < a.Cin * 16; i += TC_THREADS) s_uw[i] = a.up_wq[i];
     {
         const int lane = tid & 31;
-        const long prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;
-        const long prow1 = (lo + a.R - 1) / a.Wp;
-        for (long prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
+        const int prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;
+        const int prow1 = (lo + a.R - 1) / a.Wp;
+        for (int prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
             const int b = prow >= 0 ? (int)(prow / a.Hp) : -1;
-            const int yy = prow >= 0 ? (int)(prow - (long)b * a.Hp) : 0;
+            const int yy = prow >= 0 ? (int)(prow - b * a.Hp) : 0;
             const bool rowok = prow >= 0 && b < a.nimg && yy < a.H;
             for (int xx = lane; xx < a.Wp; xx += 32) {
-                const long pl = prow * a.Wp + xx - lo;
+                const int pl = prow * a.Wp + xx - lo;
                 if (pl < 0 || pl >= a.R) continue;
                 int pix = -1;
                 if (rowok && xx >= pad && xx < a.W + pad) {
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged_i8(const TcConvAr
     tc::tc_fence_after();
     {
         const int r = (warp & 3) * 32 + (tid & 31);
-        tc_epilogue_i8(tmem, a.N, s_mult, s_bq, a.out, (long)s_pix[(int)(m0 - lo) + r], 0);
+        tc_epilogue_i8(tmem, a.N, s_mult, s_bq, a.out, s_pix[(int)(m0 - lo) + r], 0);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -279,7 +281,8 @@ struct TcDwArgsI8 {
 };
 
 inline size_t tc_dw_i8_smem_bytes(const TcDwArgsI8 &a) {
-    return (size_t)(a.C / 16) * a.Rmax * 16 + (size_t)(a.Kpad / 16) * TC_LBO_A + (size_t)a.Kpad * a.N + 128;
+    return (size_t)(a.C / 16) * a.Rmax * 16 + (size_t)(a.Kpad / 16) * tc_dw_lbo_a(a.rows) + (size_t)(128 - a.rows) * 16 +
+           (size_t)a.Kpad * a.N + (size_t)a.Rmax * 4 + 128;
 }
 
 template <int NT>
@@ -287,7 +290,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_b, bar_done;
     __shared__ uint32_t s_tmem;
-    __shared__ int s_pix[TC_MAX_R];
     __shared__ int s_cpos[128];
     __shared__ float s_mult[256], s_bq[256];
     __shared__ __align__(16) float s_dw[10 * 256];   // [tap][C] (input scale folded in), [9] = bias
@@ -299,15 +301,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
     const uint32_t lbo_s = (uint32_t)a.Rmax * 16;
     unsigned char *sS = smem;
     unsigned char *sA = smem + (size_t)G * lbo_s;
-    unsigned char *sB = sA + (size_t)GA * TC_LBO_A;
-    const long M = (long)a.nimg * a.OH * a.OW;
-    const long m0 = (long)blockIdx.x * a.rows;
-    const long mlast = min(m0 + a.rows, M) - 1;
-    auto centre = [&](long m) -> long {
-        const int ox = (int)(m % a.OW), oy = (int)((m / a.OW) % a.OH), b = (int)(m / ((long)a.OW * a.OH));
-        return ((long)b * a.Hp + (long)oy * a.S) * a.Wp + (long)ox * a.S + 1;
+    const uint32_t lbo_a = tc_dw_lbo_a(a.rows);
+    unsigned char *sB = sA + (size_t)GA * lbo_a + (size_t)(128 - a.rows) * 16;
+    int *s_pix = reinterpret_cast<int *>(sB + (size_t)a.Kpad * a.N);
+    const int M = a.nimg * a.OH * a.OW;
+    const int m0 = blockIdx.x * a.rows;
+    const int mlast = min(m0 + a.rows, M) - 1;
+    auto centre = [&](int m) -> int {
+        const int ox = (int)(m % a.OW), oy = (int)((m / a.OW) % a.OH), b = (int)(m / (a.OW * a.OH));
+        return (b * a.Hp + oy * a.S) * a.Wp + ox * a.S + 1;
     };
-    const long lo = centre(m0) - a.Wp - 1;
+    const int lo = centre(m0) - a.Wp - 1;
     const int R = (int)(centre(mlast) + a.Wp + 1 - lo) + 1;
     if (R > a.Rmax) __trap();
 
@@ -325,21 +329,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
     for (int i = tid; i < 10 * a.C; i += TC_THREADS) s_dw[i] = i < 9 * a.C ? a.dw_w[i] : a.dw_b[i - 9 * a.C];
     {
         const int lane = tid & 31;
-        const long prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;
-        const long prow1 = (lo + R - 1) / a.Wp;
-        for (long prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
+        const int prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;
+        const int prow1 = (lo + R - 1) / a.Wp;
+        for (int prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
             const int b = prow >= 0 ? (int)(prow / a.Hp) : -1;
-            const int yy = prow >= 0 ? (int)(prow - (long)b * a.Hp) : 0;
+            const int yy = prow >= 0 ? (int)(prow - b * a.Hp) : 0;
             const bool rowok = prow >= 0 && b < a.nimg && yy < a.IH;
             for (int xx = lane; xx < a.Wp; xx += 32) {
-                const long pl = prow * a.Wp + xx - lo;
+                const int pl = prow * a.Wp + xx - lo;
                 if (pl < 0 || pl >= R) continue;
                 s_pix[pl] = (rowok && xx >= 1 && xx <= a.IW) ? (b * a.IH + yy) * a.IW + (xx - 1) : -1;
             }
         }
     }
     if (tid < 128) {
-        const long m = m0 + tid;
+        const int m = m0 + tid;
         s_cpos[tid] = (tid < a.rows && m < M) ? (int)(centre(m) - lo) : -1;
     }
     __syncthreads();
@@ -379,11 +383,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
             uint4 pk;
             pk.x = tc::pack4(q[0], q[1], q[2], q[3]);   pk.y = tc::pack4(q[4], q[5], q[6], q[7]);
             pk.z = tc::pack4(q[8], q[9], q[10], q[11]); pk.w = tc::pack4(q[12], q[13], q[14], q[15]);
-            *reinterpret_cast<uint4 *>(sA + (size_t)g_own * TC_LBO_A + (size_t)r * 16) = pk;
+            *reinterpret_cast<uint4 *>(sA + (size_t)g_own * lbo_a + (size_t)r * 16) = pk;
         }
     } else {                                  // K padding group (C = 16): zeros
         for (int r = tid / GA; r < a.rows; r += TC_THREADS / GA)
-            *reinterpret_cast<uint4 *>(sA + (size_t)g_own * TC_LBO_A + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(sA + (size_t)g_own * lbo_a + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
         const uint32_t a_addr = tc::smem_u32(sA), b_addr = tc::smem_u32(sB);
         const uint32_t lbo_b = (uint32_t)a.N * 16;
         for (int ks = 0; ks < (GA >> 1); ks++) {
-            const uint64_t ad = tc::smem_desc(a_addr + (uint32_t)(2 * ks) * TC_LBO_A, TC_LBO_A, 128);
+            const uint64_t ad = tc::smem_desc(a_addr + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
             const uint64_t bd = tc::smem_desc(b_addr + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
             tc::mma_i8(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
         }
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
     tc::tc_fence_after();
     {
         const int r = (warp & 3) * 32 + (tid & 31);
-        const long m = m0 + r;
+        const int m = m0 + r;
         TcOutI8 o{a.out, a.Ntotal, a.Ntotal, 1, nullptr, 0, 0};
         tc_epilogue_i8(tmem, a.N, s_mult, s_bq, o, (r < a.rows && m < M) ? m : -1, (int)blockIdx.y * a.N);
     }

@@ -52,6 +52,39 @@ class RetinaFace:
         rows = self.engine.detect_batch(list(imgs), threshold, self.nms_threshold)
         return [[FaceDetectInfo.from_row(r) for r in per] for per in rows]
 
+    def detectInImage(self, img: np.ndarray, threshold: float = 0.5, scales: Sequence[float] = (1.0,), flip: bool = False
+                      ) -> List[FaceDetectInfo]:
+        """what the reference leaves commented out / unused (RetinaFace.cpp:730-746, the `scales` argument of
+        RetinaFace.h:70): faces in ORIGINAL IMAGE pixels (x * scale), optionally with multi-scale + horizontal-flip test-time
+        augmentation.  ``scales``: fractions (0, 1] of the network input the image is fitted into; with ``flip`` every scale
+        is also run mirrored.  All views form one batch; the merge NMS across views runs on the GPU (rf_detect_views)."""
+        if img is None or img.size == 0:
+            return []
+        views = [(float(s), f) for s in scales for f in ((False, True) if flip else (False,))]
+        faces, _, _ = self.engine.detect_views(img, views, threshold, self.nms_threshold)
+        return [FaceDetectInfo.from_row(r) for r in faces]
+
+    @staticmethod
+    def draw(img: np.ndarray, faces: Sequence[FaceDetectInfo]) -> np.ndarray:
+        """The reference's commented-out visualisation (RetinaFace.cpp:730-741): red box outline of thickness 2, green
+        landmark dots, on a copy (:744: `clone()`), for faces in image coordinates.  Plain numpy (no OpenCV needed)."""
+        out = np.array(img, dtype=np.uint8, copy=True)
+        hh, ww = out.shape[:2]
+
+        def fill(x0, y0, x1, y1, colour):
+            x0, y0, x1, y1 = max(x0, 0), max(y0, 0), min(x1, ww), min(y1, hh)
+            if x1 > x0 and y1 > y0:
+                out[y0:y1, x0:x1] = colour
+        for f in faces:
+            x1, y1, x2, y2 = (int(round(v)) for v in f.rect)
+            for (a, b, c, d) in ((x1 - 1, y1 - 1, x2 + 1, y1 + 1), (x1 - 1, y2 - 1, x2 + 1, y2 + 1),
+                                 (x1 - 1, y1 - 1, x1 + 1, y2 + 1), (x2 - 1, y1 - 1, x2 + 1, y2 + 1)):
+                fill(a, b, c, d, (0, 0, 255))
+            for px, py in zip(f.pts_x, f.pts_y):
+                cx, cy = int(round(px)), int(round(py))
+                fill(cx - 1, cy - 1, cx + 2, cy + 2, (0, 255, 0))
+        return out
+
     @staticmethod
     def map_back_scale(img_w: int, img_h: int, net_w: int, net_h: int) -> float:
         """scale of RetinaFace.cpp:587-591: multiply coordinates by it to return to image pixels (:732-738)."""

@@ -1,6 +1,8 @@
 // RetinaFace.cpp -- see RetinaFace.h.  Everything that computes lives behind the C ABI.
 #include "RetinaFace.h"
 
+#include <cmath>
+
 #include <stdexcept>
 
 RetinaFace::RetinaFace(string &model, string network_, float nms, const RetinaFaceOptions &opt)
@@ -62,4 +64,45 @@ void RetinaFace::detectBatchImages(vector<cv::Mat> imgs, float threshold) {
             last_[start + i].assign(f, f + out_counts_[i]);
         }
     }
+}
+
+vector<FaceDetectInfo> RetinaFace::detectInImage(const Mat &img, float threshold, const vector<float> &scales, bool flip) {
+    vector<FaceDetectInfo> out;
+    if (img.empty()) return out;
+    vector<rf_view> views;
+    for (float s : scales) {
+        views.push_back(rf_view{s, 0});
+        if (flip) views.push_back(rf_view{s, 1});
+    }
+    int count = 0;
+    int rc = rf_detect_views(h_, img.data, img.cols, img.rows, (int)img.step, views.data(), (int)views.size(), threshold, nms_threshold,
+                             out_faces_.data(), &count, nullptr, nullptr);
+    if (rc != RF_OK) throw std::runtime_error(string("rf_detect_views: ") + rf_status_string(rc) + ": " + rf_last_error(h_));
+    const FaceDetectInfo *f = reinterpret_cast<const FaceDetectInfo *>(out_faces_.data());
+    out.assign(f, f + count);
+    return out;
+}
+
+Mat RetinaFace::draw(const Mat &img, const vector<FaceDetectInfo> &faces) {
+    Mat out = img.clone();     // RetinaFace.cpp:744: drawing on the caller's image would accumulate boxes
+    auto fill = [&out](int x0, int y0, int x1, int y1, unsigned char b, unsigned char g, unsigned char r) {
+        x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, out.cols); y1 = std::min(y1, out.rows);
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) {
+                unsigned char *p = out.data + (size_t)y * out.step + (size_t)x * 3;
+                p[0] = b; p[1] = g; p[2] = r;
+            }
+    };
+    for (const FaceDetectInfo &f : faces) {
+        const int x1 = (int)lroundf(f.rect.x1), y1 = (int)lroundf(f.rect.y1), x2 = (int)lroundf(f.rect.x2), y2 = (int)lroundf(f.rect.y2);
+        fill(x1 - 1, y1 - 1, x2 + 1, y1 + 1, 0, 0, 255);      // Scalar(0, 0, 255), thickness 2 (:735)
+        fill(x1 - 1, y2 - 1, x2 + 1, y2 + 1, 0, 0, 255);
+        fill(x1 - 1, y1 - 1, x1 + 1, y2 + 1, 0, 0, 255);
+        fill(x2 - 1, y1 - 1, x2 + 1, y2 + 1, 0, 0, 255);
+        for (int k = 0; k < 5; k++) {                          // Scalar(0, 255, 0) dots (:739)
+            const int cx = (int)lroundf(f.pts.x[k]), cy = (int)lroundf(f.pts.y[k]);
+            fill(cx - 1, cy - 1, cx + 2, cy + 2, 0, 255, 0);
+        }
+    }
+    return out;
 }

@@ -53,6 +53,14 @@ class RetinaFace {
     const vector<FaceDetectInfo> &lastFaces() const { return last_.empty() ? empty_ : last_[0]; }
     const vector<vector<FaceDetectInfo>> &lastBatchFaces() const { return last_; }
     float lastScale(size_t i = 0) const { return i < scales_.size() ? scales_[i] : 1.f; }
+    // SURVEY.md 8f-2 -- what the reference leaves commented out (RetinaFace.cpp:730-746) or unused (`scales`, RetinaFace.h:70):
+    // faces of ONE image in ORIGINAL IMAGE pixels (x * scale), optionally with multi-scale / horizontal-flip test-time
+    // augmentation: `scales` are fractions (0, 1] of the network input the image is fitted into; with `flip` each scale also
+    // runs mirrored.  All views run as one batch and are merged by NMS on the GPU (rf_detect_views).
+    vector<FaceDetectInfo> detectInImage(const Mat &img, float threshold = 0.5, const vector<float> &scales = vector<float>(1, 1.0f),
+                                         bool flip = false);
+    // the reference's visualisation (RetinaFace.cpp:730-741): red box outline (thickness 2), green landmark dots, on a clone
+    static Mat draw(const Mat &img, const vector<FaceDetectInfo> &faces);
     int netWidth() const { return opt_.net_w; }
     int netHeight() const { return opt_.net_h; }
 

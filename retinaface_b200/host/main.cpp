@@ -2,7 +2,7 @@
 // construct the detector from a model directory, then time detect() in a loop.  The reference
 // loops forever on a hard-coded JPEG; this one takes a raw BGR image (or synthesises noise) and
 // a finite iteration count so that it can run unattended.
-//   rf_main <model_dir> [--image raw.bgr W H] [--net W H] [--iters N] [--batch B] [--thr T]
+//   rf_main <model_dir> [--image raw.bgr W H] [--net W H] [--iters N] [--batch B] [--thr T] [--tta] [--draw out.bgr]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -22,7 +22,8 @@ int main(int argc, char **argv) {
     opt.net_w = 448; opt.net_h = 448;
     int iters = 1000, batch = 1, iw = 448, ih = 448;
     float thr = 0.9f;
-    string image;
+    string image, draw_path;
+    bool tta = false;
     for (int i = 2; i < argc; i++) {
         if (!strcmp(argv[i], "--image") && i + 3 < argc) { image = argv[i + 1]; iw = atoi(argv[i + 2]); ih = atoi(argv[i + 3]); i += 3; }
         else if (!strcmp(argv[i], "--net") && i + 2 < argc) { opt.net_w = atoi(argv[i + 1]); opt.net_h = atoi(argv[i + 2]); i += 2; }
@@ -30,6 +31,8 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "--batch") && i + 1 < argc) batch = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--thr") && i + 1 < argc) thr = (float)atof(argv[++i]);
         else if (!strcmp(argv[i], "--model") && i + 1 < argc) opt.model_file = argv[++i];
+        else if (!strcmp(argv[i], "--tta")) tta = true;
+        else if (!strcmp(argv[i], "--draw") && i + 1 < argc) draw_path = argv[++i];
     }
     opt.max_batch = batch > opt.max_batch ? batch : opt.max_batch;
     try {
@@ -56,6 +59,20 @@ int main(int argc, char **argv) {
                rf->lastFaces().size());
         for (const FaceDetectInfo &f : rf->lastFaces())
             printf("  score %.4f box [%.2f %.2f %.2f %.2f] scale %.3f\n", f.score, f.rect.x1, f.rect.y1, f.rect.x2, f.rect.y2, rf->lastScale());
+        if (tta || !draw_path.empty()) {
+            // what the reference leaves commented out (RetinaFace.cpp:730-746): faces in image pixels, drawn on a clone;
+            // --tta adds a 0.75 scale and mirrored views, merged on the GPU
+            vector<float> scales(1, 1.0f);
+            if (tta) scales.push_back(0.75f);
+            vector<FaceDetectInfo> faces = rf->detectInImage(img, thr, scales, tta);
+            printf("in image coordinates (%zu view%s): %zu faces\n", scales.size() * (tta ? 2 : 1), tta ? "s" : "", faces.size());
+            for (const FaceDetectInfo &f : faces) printf("  score %.4f box [%.2f %.2f %.2f %.2f]\n", f.score, f.rect.x1, f.rect.y1, f.rect.x2, f.rect.y2);
+            if (!draw_path.empty()) {
+                cv::Mat vis = RetinaFace::draw(img, faces);
+                std::ofstream o(draw_path, std::ios::binary);
+                for (int y = 0; y < vis.rows; y++) o.write((const char *)vis.data + (size_t)y * vis.step, (std::streamsize)vis.cols * 3);
+            }
+        }
         delete rf;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());

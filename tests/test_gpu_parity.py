@@ -521,3 +521,62 @@ def test_shipped_and_odd_network_sizes(hw, golden_image, post_oracle):
                     assert np.abs(c[1:5] - g[1:5]).max() < tol, (hw, prec, i, c[:5], g[:5])
         finally:
             eng.close()
+
+
+def test_detect_views_tta_and_map_back(golden_image, post_oracle):
+    """SURVEY.md 8f-2 (rf_detect_views): multi-scale + mirrored views of one image run as one batch, mapped back to
+    ORIGINAL IMAGE pixels (x * scale, RetinaFace.cpp:732-738) and merged by one NMS across views, all on the GPU.
+    Oracle: every view built on the host (np flip + the OpenCV letter-box oracle into the view's box), detected through
+    the plain batch path, mapped back / un-mirrored in float32 numpy and merged by the oracle NMS -- faces identical
+    bit for bit, in order.  A single (1.0, no flip) view is detect + map-back."""
+    from retinaface_b200 import RF_PREC_FP32, RfError
+    h_img, w_img = golden_image.shape[:2]
+    eng = _engine("mnet25", 448, 448, RF_PREC_FP32, max_batch=4)
+    try:
+        views = [(1.0, False), (1.0, True), (0.75, False), (0.6, True)]
+        faces, view_of, scales = eng.detect_views(golden_image, views, 0.9, 0.4)
+        cands = []
+        for v, (s, flip) in enumerate(views):
+            bw, bh = int(448 * s), int(448 * s)
+            src = np.ascontiguousarray(golden_image[:, ::-1]) if flip else golden_image
+            canvas = np.zeros((448, 448, 3), np.uint8)
+            canvas[:bh, :bw] = letterbox_bgr_u8(src, bh, bw)
+            det = eng.detect_batch([canvas], 0.9, 0.4)[0]
+            sc = max(np.float32(1.0 * w_img / bw), np.float32(1.0 * h_img / bh), np.float32(1.0))
+            assert scales[v] == sc
+            m = det.copy()
+            m[:, 1:] = det[:, 1:] * np.float32(sc)
+            if flip:
+                wm1 = np.float32(w_img - 1)
+                f = m.copy()
+                f[:, 1], f[:, 3] = wm1 - m[:, 3], wm1 - m[:, 1]
+                lx = wm1 - m[:, 5:10]
+                f[:, 5:10] = lx[:, [1, 0, 2, 4, 3]]
+                f[:, 10:15] = m[:, 10:15][:, [1, 0, 2, 4, 3]]
+                m = f
+            cands.append((v, m))
+        allc = np.concatenate([m for _, m in cands])
+        vids = np.concatenate([np.full(len(m), v, np.int32) for v, m in cands])
+        want, pos = post_oracle.nms(allc, 0.4)
+        assert len(want) >= 5 and len(cands[3][1]) >= 3        # the small mirrored view still finds faces
+        assert faces.shape == want.shape
+        assert np.array_equal(faces, want)
+        assert np.array_equal(view_of, vids[pos])
+        # single plain view == detect + map-back
+        one, _, sc1 = eng.detect_views(golden_image, [(1.0, False)], 0.9, 0.4)
+        plain = eng.detect_batch([golden_image], 0.9, 0.4)[0]
+        ref = plain.copy()
+        ref[:, 1:] = plain[:, 1:] * np.float32(sc1[0])
+        assert np.array_equal(one, ref)
+        # faces land on the photo: boxes inside the image, mirrored views agree with the plain ones within a few pixels
+        assert (faces[:, 1] >= 0).all() and (faces[:, 3] <= w_img + 2).all() and (faces[:, 4] <= h_img + 2).all()
+        m0, m1 = cands[0][1], cands[1][1]
+        for f0 in m0:
+            d = np.abs(m1[:, 1:5] - f0[1:5]).max(axis=1)
+            assert d.min() < 12.0, d.min()
+        with pytest.raises(RfError):
+            eng.detect_views(golden_image, [(1.5, False)], 0.9, 0.4)
+        with pytest.raises(RfError):
+            eng.detect_views(golden_image, [(1.0, False)] * 5, 0.9, 0.4)     # > max_batch views
+    finally:
+        eng.close()
