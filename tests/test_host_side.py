@@ -102,3 +102,21 @@ def test_calibrator_threshold_search_matches_numpy_restatement(built_lib):
         assert abs(a - b) <= 2, (a, b)          # identical up to summation-order ties between neighbouring candidates
     assert 128 <= lib(cases[2].astype(np.uint32)) < 320     # most of the sparse uniform outliers in [5, 10) (bins >= 256) are clipped
     assert lib(cases[0].astype(np.uint32)) > 300            # a half-normal keeps most of its range (no over-clipping)
+
+
+def test_detector_mirror_draw_is_the_references_visualisation():
+    """RetinaFace.draw (RetinaFace.cpp:730-741): red box outline of thickness 2 and green landmark dots on a
+    copy; clipped at the image border; the input image is left untouched."""
+    import numpy as np
+    from retinaface_b200.detector import FaceDetectInfo, RetinaFace
+    img = np.full((40, 60, 3), 7, np.uint8)
+    f = FaceDetectInfo(0.99, (10.2, 5.0, 30.0, 25.6), (15.0, 25.0, 20.0, 16.0, 24.0), (12.0, 12.0, 16.0, 21.0, 21.0))
+    g = FaceDetectInfo(0.95, (50.0, 30.0, 70.0, 50.0), (55.0,) * 5, (35.0,) * 5)          # runs over the border
+    out = RetinaFace.draw(img, [f, g])
+    assert (img == 7).all() and out.shape == img.shape
+    red = (out == (0, 0, 255)).all(axis=2)
+    green = (out == (0, 255, 0)).all(axis=2)
+    assert red[4:6, 9:31].all() and red[25:27, 9:31].all() and red[4:27, 9:11].all() and red[4:27, 29:31].all()
+    assert not red[8:24, 13:28].any()                      # outline only
+    assert green[11:14, 14:17].all() and green[20:23, 23:26].all()
+    assert red[29:31, 49:60].all() and red[29:40, 49:51].all()
