@@ -391,7 +391,19 @@ void build_plan(rf_handle h) {
                 }
             for (int c = 0; c < 8; c++)
                 for (int o = 0; o < 16; o++) b1img[(0 * 16 + o) * 8 + c] = __float2half(wp[c * 16 + o]);
-            size_t ob0img = B.add_weights_h(b0img), ob1img = B.add_weights_h(b1img);
+            // one blob for the tensor-core stem (stem_tc.cuh): B images, then the FP32 constants
+            std::vector<__half> blob(STEM_CONST_BYTES / 2, __float2half(0.f));
+            memcpy(blob.data(), b0img.data(), STEM_B0_BYTES);
+            memcpy(reinterpret_cast<unsigned char *>(blob.data()) + STEM_B0_BYTES, b1img.data(), STEM_B1_BYTES);
+            {
+                std::vector<float> fl;
+                fl.insert(fl.end(), c0.b.begin(), c0.b.begin() + 8);
+                fl.insert(fl.end(), wd.begin(), wd.end());
+                fl.insert(fl.end(), dw.b.begin(), dw.b.begin() + 8);
+                fl.insert(fl.end(), pw.b.begin(), pw.b.begin() + 16);
+                memcpy(reinterpret_cast<unsigned char *>(blob.data()) + STEM_B0_BYTES + STEM_B1_BYTES, fl.data(), STEM_F_FLOATS * 4);
+            }
+            size_t oblob = B.add_weights_h(blob);
             const bool simt_stem = (h->cfg.flags & (RF_FLAG_SIMT_STEM | RF_FLAG_NO_TENSORCORE)) != 0;
             cur = B.tensor("mobilenet0_relu2_fwd", cur_h, cur_w, 16);
             int out = cur;
@@ -406,7 +418,7 @@ void build_plan(rf_handle h) {
                     StemWeights sw{Wd(ow0), Wd(ob0), Wd(owd), Wd(obd), Wd(owp), Wd(obp)};
                     launch_k(k_stem<__half>, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), sw, n, H, W, 1.0f);
                 } else {
-                    StemTcArgs a{h->d_weights_h + ob0img, h->d_weights_h + ob1img, Wd(ob0), Wd(owd), Wd(obd), Wd(obp)};
+                    StemTcArgs a{reinterpret_cast<const unsigned char *>(h->d_weights_h + oblob)};
                     launch_k(k_stem_tc, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), a, n, H, W);
                 }
             };

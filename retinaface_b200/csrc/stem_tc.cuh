@@ -21,13 +21,16 @@
 
 namespace rf {
 
+// All constants of the kernel as ONE blob (one TMA bulk copy per CTA):
+//   [0, 2048)     conv0 B images [hi, lo][4 K-groups][16 n][8] halfs, k = (ky*3+kx)*3 + c_bgr, n >= 8 and k >= 27 zero;
+//                 w = hi + lo (two FP16 pieces, 22 significant bits) accumulated by two MMAs per K step
+//   [2048, 2560)  conv2 B image [2 K-groups][16 n][8] halfs, k = channel (k >= 8 zero)
+//   [2560, 2976)  floats: conv0 bias [8], depthwise weights [9][8], depthwise bias [8], conv2 bias [16]
+constexpr int STEM_B0_BYTES = 2 * 4 * 16 * 8 * 2, STEM_B1_BYTES = 2 * 16 * 8 * 2, STEM_F_FLOATS = 8 + 72 + 8 + 16;
+constexpr int STEM_CONST_BYTES = STEM_B0_BYTES + STEM_B1_BYTES + STEM_F_FLOATS * 4;
+static_assert(STEM_CONST_BYTES % 16 == 0, "bulk copy size");
 struct StemTcArgs {
-    const __half *b0;       // conv0 B images: [hi, lo][4 groups][16 n][8] halfs, k = (ky*3+kx)*3 + c_bgr, n >= 8 and k >= 27
-                            // zero; w = hi + lo (two FP16 pieces, 22 significant bits) accumulated by two MMAs per K step
-    const __half *b1;       // conv2 B image: [2 groups][16 n][8] halfs, k = channel (k >= 8 zero)
-    const float *bias0;     // [8]
-    const float *wd, *bd;   // depthwise [9][8], [8]
-    const float *bias2;     // [16]
+    const unsigned char *consts;     // STEM_CONST_BYTES, 16-byte aligned
 };
 
 constexpr int STEM_LBO0 = 384 * 16 + 16;    // A0: 3 tiles x 128 rows
@@ -37,12 +40,9 @@ __global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict
                                                     int n, int H, int W) {
     __shared__ __align__(16) uint8_t s_in[37][116];
     __shared__ __align__(128) unsigned char s_a0[4 * STEM_LBO0];
-    __shared__ __align__(128) __half s_b0[2 * 4 * 16 * 8];
-    __shared__ __align__(128) __half s_b1[2 * 16 * 8];
+    __shared__ __align__(128) unsigned char s_const[STEM_CONST_BYTES];
     __shared__ __align__(16) float s_c0[18 * 18][8];
-    __shared__ __align__(16) float s_wd[9 * 8 + 8];
-    __shared__ float s_bias0[8], s_bias2[16];
-    __shared__ __align__(8) uint64_t bar0, bar1;
+    __shared__ __align__(8) uint64_t bar0, bar1, bar_w;
     __shared__ uint32_t s_tmem;
 
     unsigned char *s_a1 = s_a0;      // the pointwise operand reuses conv0's (dead once bar0 has completed)
@@ -53,18 +53,19 @@ __global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict
     const int trem = blockIdx.x - b * tiles_x * tiles_y;
     const int oy0 = (trem / tiles_x) << 4, ox0 = (trem % tiles_x) << 4;
 
+    const __half *s_b0 = reinterpret_cast<const __half *>(s_const), *s_b1 = reinterpret_cast<const __half *>(s_const + STEM_B0_BYTES);
+    const float *s_bias0 = reinterpret_cast<const float *>(s_const + STEM_B0_BYTES + STEM_B1_BYTES);
+    const float *s_wd = s_bias0 + 8, *s_bias2 = s_bias0 + 8 + 72 + 8;       // s_wd[72 + c] = depthwise bias
     if (tid == 0) {
         tc::mbar_init(&bar0, 1);
         tc::mbar_init(&bar1, 1);
+        tc::mbar_init(&bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tc::mbar_expect_tx(&bar_w, STEM_CONST_BYTES);
+        tc::bulk_g2s(s_const, w.consts, STEM_CONST_BYTES, &bar_w);      // constants: independent of the previous kernel
     }
     if (warp == 1) tc::tmem_alloc<64>(&s_tmem);
     pdl_trigger();
-    for (int i = tid; i < 2 * 4 * 16 * 8 / 8; i += 256) reinterpret_cast<uint4 *>(s_b0)[i] = reinterpret_cast<const uint4 *>(w.b0)[i];
-    if (tid >= 128 && tid < 128 + 2 * 16 * 8 / 8) reinterpret_cast<uint4 *>(s_b1)[tid - 128] = reinterpret_cast<const uint4 *>(w.b1)[tid - 128];
-    for (int i = tid; i < 9 * 8 + 8; i += 256) s_wd[i] = i < 72 ? w.wd[i] : w.bd[i - 72];
-    if (tid < 8) s_bias0[tid] = w.bias0[tid];
-    if (tid < 16) s_bias2[tid] = w.bias2[tid];
     pdl_wait();
     // ---- 1. stage the u8 patch (see k_stem) ------------------------------------------------------------------
     const uint8_t *__restrict__ img = run->input + (size_t)b * H * W * 3;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict
     const uint32_t tmem = s_tmem;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // ---- 3. conv0 GEMM ----------------------------------------------------------------------------------------------
+    tc::mbar_wait(&bar_w, 0);            // the constants landed long ago; makes them visible to every thread
     if (tid == 0) {
         const uint32_t a0 = tc::smem_u32(s_a0), b0 = tc::smem_u32(s_b0);
         for (int t = 0; t < 3; t++)
@@ -160,8 +162,8 @@ __global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict
     // ---- 4. conv0 epilogue -> s_c0 (FP32), zero outside the map ---------------------------------------------------------
     for (int t = (warp >> 2); t < 3; t += 2) {
         const int p = t * 128 + (warp & 3) * 32 + lane;
-        uint32_t r[16];
-        tc::tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)t * 16, r);
+        uint32_t r[8];                      // columns 8..15 of the N = 16 tile are padding
+        tc::tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)t * 16, r);
         tc::tmem_ld_wait();
         if (p < 324) {
             const int py = p / 18, px = p - py * 18;

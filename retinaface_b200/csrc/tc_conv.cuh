@@ -105,6 +105,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t r[16]) {
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(addr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t r[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(addr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace tc
@@ -388,7 +393,7 @@ inline size_t tc_dw_smem_bytes(const TcDwArgs &a) {
 // (small C, thousands of CTAs: registers are better spent on occupancy; all lanes of a warp read the same
 // few addresses, so the shared reads are broadcasts).
 template <int NT, bool WREG>
-__global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 3) k_tc_dwpw_staged(const TcDwArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(const TcDwArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_b, bar_done;
     __shared__ uint32_t s_tmem;
