@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 RF_PREC_FP32, RF_PREC_FP16, RF_PREC_INT8 = 0, 1, 2
-RF_FLAG_NO_GRAPH, RF_FLAG_NO_TENSORCORE, RF_FLAG_SIMT_STEM = 0x1, 0x2, 0x4
+RF_FLAG_NO_GRAPH, RF_FLAG_NO_TENSORCORE, RF_FLAG_SIMT_STEM, RF_FLAG_DW_1D = 0x1, 0x2, 0x4, 0x8
 FACE_FLOATS = 15
 PIPELINE_DEPTH = 6   # RF_PIPELINE_DEPTH
 

@@ -24,6 +24,7 @@
 #include "tc_conv.cuh"
 #include "tc_conv_i8.cuh"
 #include "stem_tc.cuh"
+#include "tc_dwpw2d.cuh"
 
 using namespace rf;
 
@@ -310,6 +311,17 @@ void launch_tc_dwpw(const TcDwArgs &a, int nsplit, cudaStream_t s) {
         default: if (a.C >= 64) launch_k(k_tc_dwpw_staged<256, true>, grid, dim3(TC_THREADS), smem, s, a); else launch_k(k_tc_dwpw_staged<256, false>, grid, dim3(TC_THREADS), smem, s, a); break;
     }
 }
+void launch_tc_dwpw_2d(const TcDw2dArgs &a, cudaStream_t s) {
+    const dim3 grid((unsigned)(a.tiles_x * a.tiles_y * a.nimg));
+    const size_t smem = tc_dw2d_smem_bytes(a);
+    switch (tc_tmem_cols(a.N)) {
+        case 32: launch_k(k_tc_dwpw_2d<32>, grid, dim3(TC_THREADS), smem, s, a); break;
+        case 64: launch_k(k_tc_dwpw_2d<64>, grid, dim3(TC_THREADS), smem, s, a); break;
+        case 128: launch_k(k_tc_dwpw_2d<128>, grid, dim3(TC_THREADS), smem, s, a); break;
+        default: launch_k(k_tc_dwpw_2d<256>, grid, dim3(TC_THREADS), smem, s, a); break;
+    }
+}
+
 constexpr int TC_SMEM_LIMIT = 200 * 1024;   // dynamic; the kernels also hold ~20 KB static
 cudaError_t tc_init() {
     cudaError_t e;
@@ -318,6 +330,7 @@ cudaError_t tc_init() {
     RF_TC_ATTR((k_tc_conv_staged<32, true>)); RF_TC_ATTR((k_tc_conv_staged<64, true>)); RF_TC_ATTR((k_tc_conv_staged<128, true>)); RF_TC_ATTR((k_tc_conv_staged<256, true>));
     RF_TC_ATTR((k_tc_dwpw_staged<32, true>)); RF_TC_ATTR((k_tc_dwpw_staged<64, true>)); RF_TC_ATTR((k_tc_dwpw_staged<128, true>)); RF_TC_ATTR((k_tc_dwpw_staged<256, true>));
     RF_TC_ATTR((k_tc_dwpw_staged<32, false>)); RF_TC_ATTR((k_tc_dwpw_staged<64, false>)); RF_TC_ATTR((k_tc_dwpw_staged<128, false>)); RF_TC_ATTR((k_tc_dwpw_staged<256, false>));
+    RF_TC_ATTR(k_tc_dwpw_2d<32>); RF_TC_ATTR(k_tc_dwpw_2d<64>); RF_TC_ATTR(k_tc_dwpw_2d<128>); RF_TC_ATTR(k_tc_dwpw_2d<256>);
 #undef RF_TC_ATTR
     return cudaSuccess;
 }
@@ -478,7 +491,21 @@ void build_plan(rf_handle h) {
                 s.in = {tin}; s.out = {tpw};
                 s.flops_per_img = 2.0 * oh * ow_ * C * 9 + 2.0 * oh * ow_ * C * N;
                 s.bytes_per_img = ((double)ih * iw * C + (double)oh * ow_ * N) * es;
+                // large maps: 2-D tiles (tc_dwpw2d.cuh) -- half the staged halo, no position table, vertical reuse
+                const bool tiles2d = oh * ow_ > 28 * 28 && C >= 16 && C <= 64 && geo.nsplit == 1 && !(h->cfg.flags & RF_FLAG_DW_1D);
+                if (tiles2d) s.name = fmt("tc2d_dw%d+pw%d_s%d_%dto%d", i, i + 1, S, C, N);
                 s.launch = [=](int n, cudaStream_t st) {
+                    if (tiles2d) {
+                        TcDw2dArgs a{};
+                        a.in = T_(tin); a.C = C; a.nimg = n; a.IH = ih; a.IW = iw; a.OH = oh; a.OW = ow_; a.S = S; a.N = N;
+                        a.TH = 8;
+                        const int t16 = (ow_ + 15) / 16, t14 = (ow_ + 13) / 14;
+                        a.TW = t14 < t16 ? 14 : 16;
+                        tc_dw2d_finish(a);
+                        a.wimg = h->d_weights_h + oimg; a.bias = Wd(obp); a.dw_w = Wd(owd); a.dw_b = Wd(obd); a.out = T_(tpw);
+                        launch_tc_dwpw_2d(a, st);
+                        return;
+                    }
                     TcDwArgs a{};
                     a.in = T_(tin); a.C = C; a.nimg = n; a.IH = ih; a.IW = iw; a.OH = oh; a.OW = ow_; a.S = S;
                     a.N = N / geo.nsplit; a.Ntotal = N; a.Kpad = Kpad; a.rows = geo.rows; a.Wp = iw + 2; a.Hp = ih + 1; a.Rmax = geo.Rmax;
