@@ -432,7 +432,7 @@ void build_plan(rf_handle h) {
                     launch_k(k_stem<__half>, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), sw, n, H, W, 1.0f);
                 } else {
                     StemTcArgs a{reinterpret_cast<const unsigned char *>(h->d_weights_h + oblob)};
-                    launch_k(k_stem_tc, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), a, n, H, W);
+                    launch_k(k_stem_tc, dim3((unsigned)((W / 2 + 15) / 16), (unsigned)((H / 2 + 15) / 16), (unsigned)n), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), a, n, H, W);
                 }
             };
             B.step(std::move(s));

@@ -48,10 +48,8 @@ __global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict
     unsigned char *s_a1 = s_a0;      // the pointwise operand reuses conv0's (dead once bar0 has completed)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int OH = H >> 1, OW = W >> 1;
-    const int tiles_x = (OW + 15) >> 4, tiles_y = (OH + 15) >> 4;
-    const int b = blockIdx.x / (tiles_x * tiles_y);
-    const int trem = blockIdx.x - b * tiles_x * tiles_y;
-    const int oy0 = (trem / tiles_x) << 4, ox0 = (trem % tiles_x) << 4;
+    const int b = blockIdx.z;            // grid = (tiles_x, tiles_y, images)
+    const int oy0 = blockIdx.y << 4, ox0 = blockIdx.x << 4;
 
     const __half *s_b0 = reinterpret_cast<const __half *>(s_const), *s_b1 = reinterpret_cast<const __half *>(s_const + STEM_B0_BYTES);
     const float *s_bias0 = reinterpret_cast<const float *>(s_const + STEM_B0_BYTES + STEM_B1_BYTES);
@@ -145,8 +143,9 @@ __global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict
     const uint32_t tmem = s_tmem;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // ---- 3. conv0 GEMM ----------------------------------------------------------------------------------------------
-    tc::mbar_wait(&bar_w, 0);            // the constants landed long ago; makes them visible to every thread
+    // (waits: ONE warp polls the mbarrier; the others block in the CTA barrier, which costs no issue slots)
     if (tid == 0) {
+        tc::mbar_wait(&bar_w, 0);        // B images
         const uint32_t a0 = tc::smem_u32(s_a0), b0 = tc::smem_u32(s_b0);
         for (int t = 0; t < 3; t++)
             for (int part = 0; part < 2; part++)
@@ -157,7 +156,8 @@ __global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict
                 }
         tc::mma_commit(&bar0);
     }
-    tc::mbar_wait(&bar0, 0);
+    if (warp == 0) { tc::mbar_wait(&bar_w, 0); tc::mbar_wait(&bar0, 0); }       // constants (bias0, wd, ...) + conv0 accumulators
+    __syncthreads();
     tc::tc_fence_after();
     // ---- 4. conv0 epilogue -> s_c0 (FP32), zero outside the map ---------------------------------------------------------
     for (int t = (warp >> 2); t < 3; t += 2) {
@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict
         }
         tc::mma_commit(&bar1);
     }
-    tc::mbar_wait(&bar1, 0);
+    if (warp == 0) tc::mbar_wait(&bar1, 0);
+    __syncthreads();
     tc::tc_fence_after();
     // ---- 7. epilogue: + bias, ReLU, FP16, store ----------------------------------------------------------------------------
     {

@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
         tc::mma_commit(&bar_done);
     }
     // ---- epilogue ---------------------------------------------------------------------------------------
-    tc::mbar_wait(&bar_done, 0);
+    if (warp == 0) tc::mbar_wait(&bar_done, 0);      // one warp polls; the block barrier (no issue slots) releases the rest
+    __syncthreads();
     tc::tc_fence_after();
     {
         const int r = (warp & 3) * 32 + (tid & 31);
@@ -534,7 +535,8 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
         }
         tc::mma_commit(&bar_done);
     }
-    tc::mbar_wait(&bar_done, 0);
+    if (warp == 0) tc::mbar_wait(&bar_done, 0);      // one warp polls; the block barrier (no issue slots) releases the rest
+    __syncthreads();
     tc::tc_fence_after();
     {
         const int r = (warp & 3) * 32 + (tid & 31);

@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
         }
         tc::mma_commit(&bar_done);
     }
-    tc::mbar_wait(&bar_done, 0);
+    if (warp == 0) tc::mbar_wait(&bar_done, 0);      // one warp polls; the block barrier (no issue slots) releases the rest
+    __syncthreads();
     tc::tc_fence_after();
     {
         const int r = (warp & 3) * 32 + lane;
