@@ -491,8 +491,9 @@ void build_plan(rf_handle h) {
                 s.in = {tin}; s.out = {tpw};
                 s.flops_per_img = 2.0 * oh * ow_ * C * 9 + 2.0 * oh * ow_ * C * N;
                 s.bytes_per_img = ((double)ih * iw * C + (double)oh * ow_ * N) * es;
-                // large maps: 2-D tiles (tc_dwpw2d.cuh) -- half the staged halo, no position table, vertical reuse
-                const bool tiles2d = oh * ow_ > 28 * 28 && C >= 16 && C <= 64 && geo.nsplit == 1 && !(h->cfg.flags & RF_FLAG_DW_1D);
+                // large maps (> 56x56 outputs; measured: no gain below): 2-D tiles (tc_dwpw2d.cuh) -- half the staged halo, no position
+                // table, vertical reuse
+                const bool tiles2d = oh * ow_ > 56 * 56 && C >= 16 && C <= 64 && geo.nsplit == 1 && !(h->cfg.flags & RF_FLAG_DW_1D);
                 if (tiles2d) s.name = fmt("tc2d_dw%d+pw%d_s%d_%dto%d", i, i + 1, S, C, N);
                 s.launch = [=](int n, cudaStream_t st) {
                     if (tiles2d) {

@@ -36,16 +36,21 @@ struct StemTcArgs {
 constexpr int STEM_LBO0 = 384 * 16 + 16;    // A0: 3 tiles x 128 rows
 constexpr int STEM_LBO1 = 256 * 16 + 16;    // A1: 2 tiles x 128 rows
 
-__global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict__ run, __half *__restrict__ out, StemTcArgs w,
+__global__ void __launch_bounds__(256, 6) k_stem_tc(const PostParams *__restrict__ run, __half *__restrict__ out, StemTcArgs w,
                                                     int n, int H, int W) {
     __shared__ __align__(16) uint8_t s_in[37][116];
     __shared__ __align__(128) unsigned char s_a0[4 * STEM_LBO0];
     __shared__ __align__(128) unsigned char s_const[STEM_CONST_BYTES];
-    __shared__ __align__(16) float s_c0[18 * 18][8];
     __shared__ __align__(8) uint64_t bar0, bar1, bar_w;
     __shared__ uint32_t s_tmem;
 
-    unsigned char *s_a1 = s_a0;      // the pointwise operand reuses conv0's (dead once bar0 has completed)
+    // conv0's operand is dead once bar0 has completed: the pointwise operand (2 * STEM_LBO1 bytes) and, behind it, conv0's
+    // FP32 output ring reuse its space -- 32 KB of shared memory per CTA, 6 CTAs (48 warps) per SM
+    unsigned char *s_a1 = s_a0;
+    constexpr int STEM_C0_OFF = (2 * STEM_LBO1 + 127) / 128 * 128;
+    static_assert(STEM_C0_OFF + 18 * 18 * 8 * 4 <= 4 * STEM_LBO0, "conv0 ring must fit behind the pointwise operand");
+    // [plane = channels 0-3 | 4-7][ring position][4]: 16-byte stride between neighbouring positions, conflict-free LDS/STS.128
+    float (*s_c0)[18 * 18][4] = reinterpret_cast<float (*)[18 * 18][4]>(s_a0 + STEM_C0_OFF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int OH = H >> 1, OW = W >> 1;
     const int b = blockIdx.z;            // grid = (tiles_x, tiles_y, images)
@@ -172,34 +177,39 @@ __global__ void __launch_bounds__(256, 4) k_stem_tc(const PostParams *__restrict
             float v[8];
 #pragma unroll
             for (int o = 0; o < 8; o++) v[o] = inside ? fmaxf(__uint_as_float(r[o]) + s_bias0[o], 0.f) : 0.f;
-            *reinterpret_cast<float4 *>(&s_c0[p][0]) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4 *>(&s_c0[p][4]) = make_float4(v[4], v[5], v[6], v[7]);
+            *reinterpret_cast<float4 *>(&s_c0[0][p][0]) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(&s_c0[1][p][0]) = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
     tc::tc_fence_before();           // conv0's TMEM columns are reused by the pointwise GEMM
     __syncthreads();
-    // ---- 5. depthwise 3x3 + ReLU -> A1 (FP16, row = this thread's output pixel) -----------------------------------------
+    // ---- 5. depthwise 3x3 + ReLU -> A1 (FP16, GEMM row = pixel ty * 16 + tx) ------------------------------------------------
+    // thread = (4-channel plane, column, PAIR of output rows): 4 ring rows x 3 columns = 12 loads feed 2 outputs, the 9
+    // weight vectors of the plane are warp-uniform (broadcast).  Per output the accumulation order is (ky, kx) ascending.
     {
-        const int ty = tid >> 4, tx = tid & 15;
-        float d[8];
+        const int plane = tid >> 7, q = tid & 127;
+        const int tx = q & 15, ty = (q >> 4) << 1;
+        const float4 bv = *reinterpret_cast<const float4 *>(&s_wd[72 + plane * 4]);
+        float d0[4] = {bv.x, bv.y, bv.z, bv.w}, d1[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-        for (int c = 0; c < 8; c++) d[c] = s_wd[72 + c];
-#pragma unroll 1
-        for (int ky = 0; ky < 3; ky++)
+        for (int ry = 0; ry < 4; ry++)
 #pragma unroll
             for (int kx = 0; kx < 3; kx++) {
-                const float *src = &s_c0[(ty + ky) * 18 + tx + kx][0];
-                const float4 a0 = *reinterpret_cast<const float4 *>(src), a1 = *reinterpret_cast<const float4 *>(src + 4);
-                const float4 w0 = *reinterpret_cast<const float4 *>(&s_wd[(ky * 3 + kx) * 8]);
-                const float4 w1 = *reinterpret_cast<const float4 *>(&s_wd[(ky * 3 + kx) * 8 + 4]);
-                d[0] = fmaf(a0.x, w0.x, d[0]); d[1] = fmaf(a0.y, w0.y, d[1]); d[2] = fmaf(a0.z, w0.z, d[2]); d[3] = fmaf(a0.w, w0.w, d[3]);
-                d[4] = fmaf(a1.x, w1.x, d[4]); d[5] = fmaf(a1.y, w1.y, d[5]); d[6] = fmaf(a1.z, w1.z, d[6]); d[7] = fmaf(a1.w, w1.w, d[7]);
+                const float4 a = *reinterpret_cast<const float4 *>(&s_c0[plane][(ty + ry) * 18 + tx + kx][0]);
+                if (ry < 3) {
+                    const float4 w = *reinterpret_cast<const float4 *>(&s_wd[(ry * 3 + kx) * 8 + plane * 4]);
+                    d0[0] = fmaf(a.x, w.x, d0[0]); d0[1] = fmaf(a.y, w.y, d0[1]); d0[2] = fmaf(a.z, w.z, d0[2]); d0[3] = fmaf(a.w, w.w, d0[3]);
+                }
+                if (ry > 0) {
+                    const float4 w = *reinterpret_cast<const float4 *>(&s_wd[((ry - 1) * 3 + kx) * 8 + plane * 4]);
+                    d1[0] = fmaf(a.x, w.x, d1[0]); d1[1] = fmaf(a.y, w.y, d1[1]); d1[2] = fmaf(a.z, w.z, d1[2]); d1[3] = fmaf(a.w, w.w, d1[3]);
+                }
             }
-#pragma unroll
-        for (int c = 0; c < 8; c++) d[c] = fmaxf(d[c], 0.f);
-        Vec8<__half> hv;
-        hv.from_float(d);
-        *reinterpret_cast<uint4 *>(s_a1 + tid * 16) = hv.v;
+        const int row = ty * 16 + tx;
+        const __half2 h00 = __floats2half2_rn(fmaxf(d0[0], 0.f), fmaxf(d0[1], 0.f)), h01 = __floats2half2_rn(fmaxf(d0[2], 0.f), fmaxf(d0[3], 0.f));
+        const __half2 h10 = __floats2half2_rn(fmaxf(d1[0], 0.f), fmaxf(d1[1], 0.f)), h11 = __floats2half2_rn(fmaxf(d1[2], 0.f), fmaxf(d1[3], 0.f));
+        *reinterpret_cast<uint2 *>(s_a1 + row * 16 + plane * 8) = make_uint2(*reinterpret_cast<const uint32_t *>(&h00), *reinterpret_cast<const uint32_t *>(&h01));
+        *reinterpret_cast<uint2 *>(s_a1 + (row + 16) * 16 + plane * 8) = make_uint2(*reinterpret_cast<const uint32_t *>(&h10), *reinterpret_cast<const uint32_t *>(&h11));
         *reinterpret_cast<uint4 *>(s_a1 + STEM_LBO1 + tid * 16) = make_uint4(0, 0, 0, 0);      // K padding (channels 8..15)
     }
     tc::fence_async_smem();
