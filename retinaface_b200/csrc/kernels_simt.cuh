@@ -289,7 +289,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ run, OutT *__restrict__ out, StemWeights sw,
                                               int n, int H, int W, float out_inv_scale) {
     __shared__ __align__(4) uint8_t s_in[37][116];   // input patch rows: `mis` alignment bytes + 37 px * 3 B, as 29 words
-    __shared__ __align__(16) float s_c0[18 * 18][8];
+    __shared__ __align__(16) float s_c0[2][18 * 18][4];   // [channels 0-3 | 4-7][ring position]: 16-byte stride, conflict-free LDS.128
     __shared__ __align__(16) float s_w0[27 * 8 + 8];
     __shared__ __align__(16) float s_wd[9 * 8 + 8];
     __shared__ __align__(16) float s_wp[8 * 16 + 16];
@@ -358,8 +358,8 @@ __global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ 
 #pragma unroll
             for (int o = 0; o < 8; o++) acc[o] = fmaxf(acc[o], 0.f);
         }
-        *reinterpret_cast<float4 *>(&s_c0[p][0]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4 *>(&s_c0[p][4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        *reinterpret_cast<float4 *>(&s_c0[0][p][0]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4 *>(&s_c0[1][p][0]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
     __syncthreads();
     // ---- depthwise 3x3 + pointwise 8->16 for this thread's pixel ------------------------------------------
@@ -373,8 +373,8 @@ __global__ void __launch_bounds__(256, 3) k_stem(const PostParams *__restrict__ 
     for (int ky = 0; ky < 3; ky++)
 #pragma unroll
         for (int kx = 0; kx < 3; kx++) {
-            const float *src = &s_c0[(ty + ky) * 18 + tx + kx][0];
-            const float4 a0 = *reinterpret_cast<const float4 *>(src), a1 = *reinterpret_cast<const float4 *>(src + 4);
+            const int pos = (ty + ky) * 18 + tx + kx;
+            const float4 a0 = *reinterpret_cast<const float4 *>(&s_c0[0][pos][0]), a1 = *reinterpret_cast<const float4 *>(&s_c0[1][pos][0]);
             const float4 w0 = *reinterpret_cast<const float4 *>(&s_wd[(ky * 3 + kx) * 8]);
             const float4 w1 = *reinterpret_cast<const float4 *>(&s_wd[(ky * 3 + kx) * 8 + 4]);
             d[0] = fmaf(a0.x, w0.x, d[0]); d[1] = fmaf(a0.y, w0.y, d[1]); d[2] = fmaf(a0.z, w0.z, d[2]); d[3] = fmaf(a0.w, w0.w, d[3]);

@@ -298,9 +298,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
     const int G = a.C >> 4;
     const int GA = a.Kpad >> 4;
     const int g_own = tid % GA;
-    const uint32_t lbo_s = (uint32_t)a.Rmax * 16;
+    const int pix = a.C;                 // staged range is pixel-major, [position][C] int8 (see k_tc_dwpw_staged)
     unsigned char *sS = smem;
-    unsigned char *sA = smem + (size_t)G * lbo_s;
+    unsigned char *sA = smem + (size_t)a.Rmax * pix;
     const uint32_t lbo_a = tc_dw_lbo_a(a.rows);
     unsigned char *sB = sA + (size_t)GA * lbo_a + (size_t)(128 - a.rows) * 16;
     int *s_pix = reinterpret_cast<int *>(sB + (size_t)a.Kpad * a.N);
@@ -351,8 +351,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
     const int lg = 31 - __clz(G);
     for (int it = tid; it < R * G; it += TC_THREADS) {
         const int g = it & (G - 1), pl = it >> lg;
-        const int pix = s_pix[pl];
-        cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (pix >= 0 ? (size_t)pix * a.C + g * 16 : 0), pix >= 0);
+        const int src_pix = s_pix[pl];
+        cp_async16_zfill(sS + (size_t)it * 16, a.in + (src_pix >= 0 ? (size_t)src_pix * a.C + g * 16 : 0), src_pix >= 0);
     }
     cp_async_wait_all();
     __syncthreads();
@@ -365,12 +365,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
             float acc[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) acc[i] = s_dw[9 * a.C + c0 + i];
-            const unsigned char *base = sS + (size_t)g_own * lbo_s + (size_t)cp * 16;
+            const unsigned char *base = sS + cp * pix + g_own * 16;
 #pragma unroll
             for (int t = 0; t < 9; t++) {
                 const int shift = (t / 3 - 1) * a.Wp + (t % 3 - 1);
                 float f[16];
-                tc::unpack16(*reinterpret_cast<const uint4 *>(base + shift * 16), f);
+                tc::unpack16(*reinterpret_cast<const uint4 *>(base + shift * pix), f);
                 const float *w = &s_dw[t * a.C + c0];
                 // separate multiply and add (no FMA): bit-identical to the integer oracle's float32 arithmetic, so a
                 // rounding flip here cannot be amplified by the following integer GEMM into a multi-LSB difference

@@ -21,29 +21,28 @@ struct TcDw2dArgs {
     int TH, TW;             // output tile, TH * TW <= 128, TH even
     int tiles_x, tiles_y;
     int PH, PW;             // staged window: (TH-1)*S+3 x (TW-1)*S+3   (tc_dw2d_finish)
-    uint32_t lbo_s, lbo_a;  // group strides of the staged window / the A operand, bytes (tc_dw2d_finish)
+    uint32_t lbo_a;         // group stride of the A operand, bytes (tc_dw2d_finish)
     const __half *wimg;     // [C/8][N][8]
     const float *bias;      // [N]
     const float *dw_w, *dw_b;   // [9][C], [C]
     __half *out;            // [nimg][OH][OW][N]
 };
 
-// Derived geometry, computed once on the host.  Group strides in 16-byte units are chosen so that the 8 lanes of a quarter
-// warp -- (group, column) pairs with the group fastest -- hit 8 different 16-byte bank groups: stride mod 8 == 8 / G
-// (G = C/8 in {2, 4, 8}).
+// Derived geometry, computed once on the host.  The staged window is PIXEL-major, [PH][PW][C] -- a byte-for-byte copy of the
+// NHWC rows it comes from: consecutive cp.async lanes write consecutive shared addresses (one wavefront per 128 bytes; a
+// channel-group-major layout scatters every 16-byte piece into its own wavefront), and the stencil's lanes -- (group, column)
+// with the group fastest -- read consecutive 16-byte pieces.  The A operand's group stride in 16-byte units is 8/G mod 8, so
+// that the 8 lanes of a quarter warp hit 8 different bank groups.
 inline void tc_dw2d_finish(TcDw2dArgs &a) {
     const int G = a.C >> 3;
     a.PH = (a.TH - 1) * a.S + 3;
     a.PW = (a.TW - 1) * a.S + 3;
     a.tiles_x = (a.OW + a.TW - 1) / a.TW;
     a.tiles_y = (a.OH + a.TH - 1) / a.TH;
-    int L = a.PH * a.PW;
-    while ((L & 7) != (8 / G)) L++;
-    a.lbo_s = (uint32_t)L * 16;
     a.lbo_a = (uint32_t)(128 + 8 / G) * 16;
 }
 inline size_t tc_dw2d_smem_bytes(const TcDw2dArgs &a) {
-    return (size_t)(a.C / 8) * a.lbo_s + (size_t)(a.C / 8) * a.lbo_a + (size_t)a.C * a.N * 2 + 128;
+    return (size_t)a.PH * a.PW * a.C * 2 + (size_t)(a.C / 8) * a.lbo_a + (size_t)a.C * a.N * 2 + 128;
 }
 
 template <int NT>
@@ -57,9 +56,10 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = a.C >> 3, lg = 31 - __clz(G);
     const int PH = a.PH, PW = a.PW;
-    const uint32_t lbo_s = a.lbo_s, lbo_a = a.lbo_a;
+    const uint32_t lbo_a = a.lbo_a;
+    const int pix = a.C * 2;             // bytes per staged pixel
     unsigned char *sS = smem;
-    unsigned char *sA = smem + (size_t)G * lbo_s;
+    unsigned char *sA = smem + (size_t)PH * PW * pix;
     unsigned char *sB = sA + (size_t)G * lbo_a;
     const int tiles = a.tiles_x * a.tiles_y;
     const int b = blockIdx.x / tiles, trem = blockIdx.x - b * tiles;
@@ -90,11 +90,11 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
             const int iy = iy0 + py;
             const bool rowok = iy >= 0 && iy < a.IH;
             const __half *src_row = a.in + (ptrdiff_t)(((b * a.IH + (rowok ? iy : 0)) * a.IW + ix0) * a.C);
-            unsigned char *dst_row = sS + py * PW * 16;
+            unsigned char *dst_row = sS + py * PW * pix;
             for (int i = lane; i < per_row; i += 32) {
-                const int px = i >> lg, g = i & (G - 1);
+                const int px = i >> lg;
                 const bool ok = rowok && px >= px_lo && px < px_hi;
-                cp_async16_zfill(dst_row + g * lbo_s + px * 16, src_row + (ok ? i * 8 : -ix0 * a.C), ok);
+                cp_async16_zfill(dst_row + i * 16, src_row + (ok ? i * 8 : -ix0 * a.C), ok);
             }
         }
     }
@@ -116,13 +116,13 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
 #pragma unroll
                 for (int i = 0; i < 8; i++) acc1[i] = acc0[i];
             }
-            const unsigned char *base = sS + (size_t)g * lbo_s + (size_t)(ty * PW + tx) * 16;
+            const unsigned char *base = sS + (ty * PW + tx) * pix + g * 16;
 #pragma unroll 1                     // (uniform branches on ry; keeps the 12 window loads from being hoisted into 48 registers)
             for (int ry = 0; ry < 4; ry++) {
 #pragma unroll
                 for (int kx = 0; kx < 3; kx++) {
                     Vec8<__half> x;
-                    x.v = *reinterpret_cast<const uint4 *>(base + (size_t)(ry * PW + kx) * 16);
+                    x.v = *reinterpret_cast<const uint4 *>(base + (ry * PW + kx) * pix);
                     float f[8];
                     x.to_float(f);
                     if (ry < 3) {        // output row ty: kernel row ry
@@ -156,11 +156,11 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
                 const float4 b0 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g * 8]), b1 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g * 8 + 4]);
                 acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
             }
-            const unsigned char *base = sS + (size_t)g * lbo_s + (size_t)(ty * a.S * PW + tx * a.S) * 16;
+            const unsigned char *base = sS + (ty * a.S * PW + tx * a.S) * pix + g * 16;
 #pragma unroll
             for (int t = 0; t < 9; t++) {
                 Vec8<__half> x;
-                x.v = *reinterpret_cast<const uint4 *>(base + (size_t)((t / 3) * PW + (t % 3)) * 16);
+                x.v = *reinterpret_cast<const uint4 *>(base + ((t / 3) * PW + (t % 3)) * pix);
                 float f[8];
                 x.to_float(f);
                 const float4 w0 = *reinterpret_cast<const float4 *>(&s_dw[t * a.C + g * 8]), w1 = *reinterpret_cast<const float4 *>(&s_dw[t * a.C + g * 8 + 4]);
