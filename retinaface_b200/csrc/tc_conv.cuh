@@ -261,32 +261,46 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     pdl_wait();                          // everything above is independent of the previous kernel's output
     // ---- stage the range: item = (position, 8-channel group), 16 B each --------------------------------
     const int lg = 31 - __clz(G);        // G is a power of two (Cin in {16, 64, 128, 256})
-    // lanes run over the channel groups of one pixel first: 16-byte pieces of a pixel are contiguous in global memory (fully
-    // used L2 sectors) but land in G different group planes of the K-major operand (one shared wavefront each).  The other
-    // order -- positions fastest, contiguous shared stores, 16-byte reads at pixel stride -- measured slower (up to 1.6x on the
-    // 1x1 convs with Cin = 256)
-    for (int it = tid; it < a.R * G; it += TC_THREADS) {
-        const int g = it & (G - 1), pl = it >> lg;
-        const int off = s_off[pl];
-        cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (off >= 0 ? off + g * 8 : 0), off >= 0);
+    // lanes run over the channel groups of one pixel first: the 16-byte pieces of a pixel are contiguous in global memory
+    // (fully used L2 sectors) and land in G different group planes of the K-major operand.  (Positions fastest -- 16-byte
+    // reads at pixel stride -- measured up to 1.6x slower on the 1x1 convs with Cin = 256.)
+    const int UH = a.H >> 1, UW = a.W >> 1;
+    unsigned char *sC = sB + (size_t)a.taps * a.Cin * a.N * 2;      // UPADD: coarse rows, pixel-major [coarse position][Cin]
+    const int crow_lo = UPADD ? s_crow[0] : 0, crow_hi = UPADD ? s_crow[1] : -1;
+    if (UPADD && crow_hi >= crow_lo) {
+        // FPN merge: staged := lateral + crop(deconv_k4s2p1(up)).  The coarse rows the tile needs (one contiguous range of the
+        // coarse map: global coarse rows [crow_lo, crow_hi]) go first, asynchronously and as a plain copy (contiguous shared
+        // stores), so that all global traffic of the tile is in flight at once
+        const int ncp = (crow_hi - crow_lo + 1) * UW;
+        if (ncp > a.Cmax) __trap();
+        const __half *csrc = a.up + (size_t)crow_lo * UW * a.Cin;
+        for (int it = tid; it < ncp * G; it += TC_THREADS) cp_async16_zfill(sC + (size_t)it * 16, csrc + (size_t)it * 8, true);
     }
-    if (UPADD) {
-        // FPN merge: staged := lateral + crop(deconv_k4s2p1(up)).  The coarse rows the tile needs are staged
-        // with cp.async as well (one more contiguous range: global coarse rows [crow_lo, crow_hi]), so all global
-        // traffic of the tile is in flight at once; the add then runs shared -> shared, in the same operation
-        // order as k_upsample_add (kernels_simt.cuh): the staged FP16 values equal the unfused Eltwise tensor.
-        const int UH = a.H >> 1, UW = a.W >> 1;
-        unsigned char *sC = sB + (size_t)a.taps * a.Cin * a.N * 2;
-        const uint32_t lbo_c = (uint32_t)a.Cmax * 16;
-        const int crow_lo = s_crow[0], crow_hi = s_crow[1];
-        if (crow_hi >= crow_lo) {
-            const int ncp = (crow_hi - crow_lo + 1) * UW;
-            if (ncp > a.Cmax) __trap();
-            for (int it = tid; it < ncp * G; it += TC_THREADS) {
-                const int g = it & (G - 1), cp = it >> lg;
-                cp_async16_zfill(sC + (size_t)g * lbo_c + (size_t)cp * 16, a.up + ((size_t)crow_lo * UW + cp) * a.Cin + g * 8, true);
+    {
+        // through registers: LDG.128 (coalesced) then STS.128 -- with R odd the 8 lanes of a quarter warp (8 groups of one
+        // pixel) hit 8 different bank groups, so the store costs the ideal 4 wavefronts per warp instead of cp.async's 32
+        constexpr int UNR = 4;
+        for (int it0 = tid; it0 < a.R * G; it0 += TC_THREADS * UNR) {
+            uint4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int it = it0 + u * TC_THREADS;
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (it < a.R * G) {
+                    const int off = s_off[it >> lg];
+                    if (off >= 0) v[u] = __ldcg(reinterpret_cast<const uint4 *>(a.in + off + (it & (G - 1)) * 8));     // L2 only, like cp.async.cg
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int it = it0 + u * TC_THREADS;
+                if (it < a.R * G) *reinterpret_cast<uint4 *>(sS + (size_t)(it & (G - 1)) * lbo_s + (size_t)(it >> lg) * 16) = v[u];
             }
         }
+    }
+    if (UPADD) {
+        // the add runs shared -> shared, in the same operation order as k_upsample_add (kernels_simt.cuh): the staged FP16
+        // values equal the unfused Eltwise tensor
         cp_async_wait_all();
         __syncthreads();
         for (int it = tid; it < a.R * G; it += TC_THREADS) {
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
                 for (int dj = 0; dj < 2; dj++) {
                     const int j = j_hi - dj, kx = x - 2 * j + 1;
                     if (j < 0 || j >= UW || kx < 0 || kx > 3) continue;
-                    const uint4 uv = *reinterpret_cast<const uint4 *>(sC + (size_t)g * lbo_c + (size_t)((b * UH + i - crow_lo) * UW + j) * 16);
+                    const uint4 uv = *reinterpret_cast<const uint4 *>(sC + ((size_t)((b * UH + i - crow_lo) * UW + j) * G + g) * 16);
                     const uint4 wv = *reinterpret_cast<const uint4 *>(&s_uw[(ky * 4 + kx) * 64 + c0]);
                     const __half2 *u2 = reinterpret_cast<const __half2 *>(&uv), *w2 = reinterpret_cast<const __half2 *>(&wv);
 #pragma unroll

@@ -170,26 +170,37 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged_i8(const TcConvAr
     __syncthreads();
     pdl_wait();
     const int lgs = 31 - __clz(GS);
-    for (int it = tid; it < a.R * GS; it += TC_THREADS) {
-        const int g = it & (GS - 1), pl = it >> lgs;
-        const int pix = s_pix[pl];
-        const bool ok = pix >= 0 && g < G;
-        cp_async16_zfill(sS + (size_t)g * lbo_s + (size_t)pl * 16, a.in + (ok ? (size_t)pix * a.Cin + g * 16 : 0), ok);
+    const int UH = a.H >> 1, UW = a.W >> 1;
+    const int lg = 31 - __clz(G);
+    unsigned char *sC = sB + (size_t)a.taps * GS * 16 * a.N;      // UPADD: coarse rows, pixel-major [coarse position][Cin]
+    const int crow_lo = UPADD ? s_crow[0] : 0, crow_hi = UPADD ? s_crow[1] : -1;
+    if (UPADD && crow_hi >= crow_lo) {       // coarse rows first: asynchronous plain copy (see k_tc_conv_staged)
+        const int ncp = (crow_hi - crow_lo + 1) * UW;
+        if (ncp > a.Cmax) __trap();
+        const int8_t *csrc = a.up + (size_t)crow_lo * UW * a.Cin;
+        for (int it = tid; it < ncp * G; it += TC_THREADS) cp_async16_zfill(sC + (size_t)it * 16, csrc + (size_t)it * 16, true);
     }
-    if (UPADD) {
-        const int UH = a.H >> 1, UW = a.W >> 1;
-        const int lg = 31 - __clz(G);
-        unsigned char *sC = sB + (size_t)a.taps * GS * 16 * a.N;
-        const uint32_t lbo_c = (uint32_t)a.Cmax * 16;
-        const int crow_lo = s_crow[0], crow_hi = s_crow[1];
-        if (crow_hi >= crow_lo) {
-            const int ncp = (crow_hi - crow_lo + 1) * UW;
-            if (ncp > a.Cmax) __trap();
-            for (int it = tid; it < ncp * G; it += TC_THREADS) {
-                const int g = it & (G - 1), cp = it >> lg;
-                cp_async16_zfill(sC + (size_t)g * lbo_c + (size_t)cp * 16, a.up + ((size_t)crow_lo * UW + cp) * a.Cin + g * 16, true);
+    {   // the range itself through registers: coalesced LDG.128, conflict-free STS.128 into the K-major operand (R is odd)
+        constexpr int UNR = 4;
+        for (int it0 = tid; it0 < a.R * GS; it0 += TC_THREADS * UNR) {
+            uint4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int it = it0 + u * TC_THREADS;
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (it < a.R * GS) {
+                    const int g = it & (GS - 1), pix = s_pix[it >> lgs];
+                    if (pix >= 0 && g < G) v[u] = __ldcg(reinterpret_cast<const uint4 *>(a.in + (size_t)pix * a.Cin + g * 16));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int it = it0 + u * TC_THREADS;
+                if (it < a.R * GS) *reinterpret_cast<uint4 *>(sS + (size_t)(it & (GS - 1)) * lbo_s + (size_t)(it >> lgs) * 16) = v[u];
             }
         }
+    }
+    if (UPADD) {
         cp_async_wait_all();
         __syncthreads();
         for (int it = tid; it < a.R * G; it += TC_THREADS) {
@@ -214,7 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged_i8(const TcConvAr
                     const int j = j_hi - dj, kx = x - 2 * j + 1;
                     if (j < 0 || j >= UW || kx < 0 || kx > 3) continue;
                     float u[16];
-                    tc::unpack16(*reinterpret_cast<const uint4 *>(sC + (size_t)g * lbo_c + (size_t)((b * UH + i - crow_lo) * UW + j) * 16), u);
+                    tc::unpack16(*reinterpret_cast<const uint4 *>(sC + ((size_t)((b * UH + i - crow_lo) * UW + j) * G + g) * 16), u);
                     const float *w = &s_uw[(ky * 4 + kx) * a.Cin + c0];
 #pragma unroll
                     for (int c = 0; c < 16; c++) acc[c] = __fadd_rn(acc[c], __fmul_rn(u[c], w[c]));   // no FMA: matches the oracle bit for bit
