@@ -1493,6 +1493,23 @@ static int fetch_results(rf_handle h, int n, rf_face *out_faces, int *out_counts
     return RF_OK;
 }
 
+// One caller image of arbitrary size -> d_raw (packed rows) on the handle's stream.  Pinned sources (cudaHostAlloc /
+// cudaHostRegister) are copied straight from the caller's memory, row stride and all, with no host synchronisation: the
+// stream orders the copy behind the letter-box kernel that still reads the previous image.  Pageable sources go through
+// the library's single pinned buffer (one host memcpy per image: ~10x the cost of the DMA itself).
+static void upload_raw(rf_handle h, const uint8_t *src, int width, int height, int row_stride) {
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    if (pinned) {
+        CK(cudaMemcpy2DAsync(h->d_raw, (size_t)width * 3, src, (size_t)row_stride, (size_t)width * 3, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+        return;
+    }
+    cudaGetLastError();
+    CK(cudaStreamSynchronize(h->stream));  // h_raw is single-buffered
+    for (int y = 0; y < height; y++) memcpy(h->h_raw + (size_t)y * width * 3, src + (size_t)y * row_stride, (size_t)width * 3);
+    CK(cudaMemcpyAsync(h->d_raw, h->h_raw, (size_t)width * height * 3, cudaMemcpyHostToDevice, h->stream));
+}
+
 int rf_detect_batch(rf_handle h, const uint8_t *const *imgs, const int *widths, const int *heights, const int *row_strides,
                     int n, float thr, float nms, rf_face *out_faces, int *out_counts, int32_t *out_idx) {
     int rc = check_n(h, n);
@@ -1541,9 +1558,7 @@ int rf_detect_batch(rf_handle h, const uint8_t *const *imgs, const int *widths, 
                 if (widths[i] > h->cfg.max_image_w || heights[i] > h->cfg.max_image_h)
                     return fail(h, RF_ERR_CAPACITY, fmt("image %d is %dx%d, larger than max_image %dx%d", i, widths[i], heights[i],
                                                         h->cfg.max_image_w, h->cfg.max_image_h));
-                CK(cudaStreamSynchronize(h->stream));  // h_raw is single-buffered
-                for (int y = 0; y < heights[i]; y++) memcpy(h->h_raw + (size_t)y * widths[i] * 3, imgs[i] + (size_t)y * rs, (size_t)widths[i] * 3);
-                CK(cudaMemcpyAsync(h->d_raw, h->h_raw, (size_t)widths[i] * heights[i] * 3, cudaMemcpyHostToDevice, h->stream));
+                upload_raw(h, imgs[i], widths[i], heights[i], rs);
                 launch_letterbox(h->d_raw, widths[i], heights[i], h->d_input + (size_t)i * img_bytes, Wn, Hn, h->stream);
             }
         }
@@ -1677,9 +1692,7 @@ int rf_detect_views(rf_handle h, const uint8_t *bgr, int width, int height, int 
         CK(cudaSetDevice(h->device));
         switch_ctx(h, 0);
         ensure_merge_buffers(h);
-        CK(cudaStreamSynchronize(h->stream));          // h_raw is single-buffered
-        for (int y = 0; y < height; y++) memcpy(h->h_raw + (size_t)y * width * 3, bgr + (size_t)y * rs, (size_t)width * 3);
-        CK(cudaMemcpyAsync(h->d_raw, h->h_raw, (size_t)width * height * 3, cudaMemcpyHostToDevice, h->stream));
+        upload_raw(h, bgr, width, height, rs);
         ViewSet vs{};
         vs.nviews = nviews;
         vs.img_w_minus1 = (float)(width - 1);
@@ -1714,9 +1727,7 @@ int rf_preprocess(rf_handle h, const uint8_t *bgr, int width, int height, int ro
     try {
         CK(cudaSetDevice(h->device));
         switch_ctx(h, 0);
-        CK(cudaStreamSynchronize(h->stream));
-        for (int y = 0; y < height; y++) memcpy(h->h_raw + (size_t)y * width * 3, bgr + (size_t)y * rs, (size_t)width * 3);
-        CK(cudaMemcpyAsync(h->d_raw, h->h_raw, (size_t)width * height * 3, cudaMemcpyHostToDevice, h->stream));
+        upload_raw(h, bgr, width, height, rs);
         launch_letterbox(h->d_raw, width, height, h->d_input, Wn, Hn, h->stream);
         CK(cudaMemcpyAsync(h->h_input, h->d_input, (size_t)Hn * Wn * 3, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));

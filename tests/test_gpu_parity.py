@@ -598,3 +598,25 @@ def test_detect_views_tta_and_map_back(golden_image, post_oracle):
             eng.detect_views(golden_image, [(1.0, False)] * 5, 0.9, 0.4)     # > max_batch views
     finally:
         eng.close()
+
+
+def test_pinned_arbitrary_size_images_take_the_direct_copy_path(golden_image):
+    """Caller images that are not network-sized: from pinned memory they are DMA-ed straight out of the caller's buffer
+    (no host staging copy, no host synchronisation per image); results equal the pageable path's, image by image."""
+    import torch
+    from retinaface_b200 import RF_PREC_FP16
+    eng = _engine("mnet25", 448, 448, RF_PREC_FP16, max_batch=4, max_image=(1024, 1280))
+    try:
+        other = np.ascontiguousarray(golden_image[100:700, 200:1100])           # a second size, 900x600
+        want = eng.detect_batch([golden_image, other, golden_image], 0.9, 0.4)
+        pins = []
+        for im in (golden_image, other, golden_image):
+            t = torch.empty(im.shape, dtype=torch.uint8).pin_memory()
+            t.numpy()[:] = im
+            pins.append(t)
+        got = eng.detect_batch([t.numpy() for t in pins], 0.9, 0.4)
+        assert [len(x) for x in got] == [len(x) for x in want] and len(got[0]) == 5
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+    finally:
+        eng.close()

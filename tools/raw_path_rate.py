@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Rate of the arbitrary-size-image path (the reference's RetinaFace::detect on camera frames): 8 x 1280x886 BGR photos per
+call through rf_detect_batch (GPU letter-box), from pageable and from pinned caller memory.  Prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    import cv2
+    import torch
+    from retinaface_b200 import RF_PREC_FP16, Engine
+    img = cv2.imread(os.path.join(bench.GOLD, "data", "img.jpg"))
+    eng = Engine(os.path.join(bench.GOLD, "weights", "mnet25.caffemodel"), 448, 448, precision=RF_PREC_FP16, max_batch=8, max_faces=128,
+                 max_image=(1024, 1280))
+    out = {"image": "%dx%d" % (img.shape[1], img.shape[0]), "batch": 8}
+    pins = [torch.empty(img.shape, dtype=torch.uint8).pin_memory() for _ in range(8)]
+    for t in pins:
+        t.numpy()[:] = img
+    for name, imgs in (("pageable", [img.copy() for _ in range(8)]), ("pinned", [t.numpy() for t in pins])):
+        for _ in range(5):
+            r = eng.detect_batch(imgs, 0.9, 0.4)
+        t0 = time.perf_counter()
+        n = 100
+        for _ in range(n):
+            r = eng.detect_batch(imgs, 0.9, 0.4)
+        dt = (time.perf_counter() - t0) / n
+        out[name] = {"ms_per_batch": dt * 1e3, "images_per_s": 8 / dt, "faces_in_image0": int(len(r[0]))}
+    eng.close()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
