@@ -25,6 +25,7 @@
 #include "tc_conv_i8.cuh"
 #include "stem_tc.cuh"
 #include "tc_dwpw2d.cuh"
+#include "tc_dwpw2d_i8.cuh"
 
 using namespace rf;
 
@@ -811,6 +812,17 @@ void launch_tc_conv_i8(const TcConvArgsI8 &a, cudaStream_t s) {
     }
 #undef RF_I8C
 }
+void launch_tc_dwpw_2d_i8(const TcDw2dArgsI8 &a, cudaStream_t s) {
+    const dim3 grid((unsigned)a.tiles_x, (unsigned)a.tiles_y, (unsigned)a.nimg);
+    const size_t smem = tc_dw2d_i8_smem_bytes(a);
+    switch (tc_tmem_cols(a.N)) {
+        case 32: launch_k(k_tc_dwpw_2d_i8<32>, grid, dim3(TC_THREADS), smem, s, a); break;
+        case 64: launch_k(k_tc_dwpw_2d_i8<64>, grid, dim3(TC_THREADS), smem, s, a); break;
+        case 128: launch_k(k_tc_dwpw_2d_i8<128>, grid, dim3(TC_THREADS), smem, s, a); break;
+        default: launch_k(k_tc_dwpw_2d_i8<256>, grid, dim3(TC_THREADS), smem, s, a); break;
+    }
+}
+
 void launch_tc_dwpw_i8(const TcDwArgsI8 &a, int nsplit, cudaStream_t s) {
     const long M = (long)a.nimg * a.OH * a.OW;
     const dim3 grid((unsigned)((M + a.rows - 1) / a.rows), nsplit);
@@ -828,6 +840,7 @@ cudaError_t tc_init_i8() {
     RF_TC_ATTR((k_tc_conv_staged_i8<32, false>)); RF_TC_ATTR((k_tc_conv_staged_i8<64, false>)); RF_TC_ATTR((k_tc_conv_staged_i8<128, false>)); RF_TC_ATTR((k_tc_conv_staged_i8<256, false>));
     RF_TC_ATTR((k_tc_conv_staged_i8<32, true>)); RF_TC_ATTR((k_tc_conv_staged_i8<64, true>)); RF_TC_ATTR((k_tc_conv_staged_i8<128, true>)); RF_TC_ATTR((k_tc_conv_staged_i8<256, true>));
     RF_TC_ATTR(k_tc_dwpw_staged_i8<32>); RF_TC_ATTR(k_tc_dwpw_staged_i8<64>); RF_TC_ATTR(k_tc_dwpw_staged_i8<128>); RF_TC_ATTR(k_tc_dwpw_staged_i8<256>);
+    RF_TC_ATTR(k_tc_dwpw_2d_i8<32>); RF_TC_ATTR(k_tc_dwpw_2d_i8<64>); RF_TC_ATTR(k_tc_dwpw_2d_i8<128>); RF_TC_ATTR(k_tc_dwpw_2d_i8<256>);
 #undef RF_TC_ATTR
     return cudaSuccess;
 }
@@ -924,7 +937,20 @@ void build_plan_i8(rf_handle h) {
         s.in = {tin}; s.out = {tpw};
         s.flops_per_img = 2.0 * oh * ow_ * C * 9 + 2.0 * oh * ow_ * C * N;
         s.bytes_per_img = (double)ih * iw * C + (double)oh * ow_ * N;
+        const bool tiles2d = oh * ow_ > 56 * 56 && C >= 16 && C <= 64 && geo.nsplit == 1 && !(h->cfg.flags & RF_FLAG_DW_1D);   // as the FP16 plan
+        if (tiles2d) s.name = fmt("i8_2d_dw%d+pw%d_s%d_%dto%d", i, i + 1, S, C, N);
         s.launch = [=](int n, cudaStream_t st) {
+            if (tiles2d) {
+                TcDw2dArgsI8 a{};
+                a.in = Q_(tin); a.C = C; a.nimg = n; a.IH = ih; a.IW = iw; a.OH = oh; a.OW = ow_; a.S = S; a.N = N; a.Kpad = Kpad;
+                a.TH = 8;
+                a.TW = (ow_ + 13) / 14 < (ow_ + 15) / 16 ? 14 : 16;
+                tc_dw2d_i8_finish(a);
+                a.wimg = h->d_weights_q + oimg; a.mult = Wd(omul); a.bq = Wd(obq); a.dw_w = Wd(owd); a.dw_b = Wd(obd); a.inv_mid = inv_mid;
+                a.out = Q_(tpw);
+                launch_tc_dwpw_2d_i8(a, st);
+                return;
+            }
             TcDwArgsI8 a{};
             a.in = Q_(tin); a.C = C; a.nimg = n; a.IH = ih; a.IW = iw; a.OH = oh; a.OW = ow_; a.S = S;
             a.N = N / geo.nsplit; a.Ntotal = N; a.Kpad = Kpad; a.rows = geo.rows; a.Wp = iw + 2; a.Hp = ih + 1; a.Rmax = geo.Rmax;
