@@ -52,6 +52,16 @@ __device__ __forceinline__ void unpack16(const uint4 &v, float f[16]) {
         f[4 * i + 3] = (float)(int8_t)(w[i] >> 24);
     }
 }
+__device__ __forceinline__ void unpack8(const uint2 &v, float f[8]) {
+    const uint32_t w[2] = {v.x, v.y};
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        f[4 * i + 0] = (float)(int8_t)(w[i] & 0xff);
+        f[4 * i + 1] = (float)(int8_t)((w[i] >> 8) & 0xff);
+        f[4 * i + 2] = (float)(int8_t)((w[i] >> 16) & 0xff);
+        f[4 * i + 3] = (float)(int8_t)(w[i] >> 24);
+    }
+}
 }  // namespace tc
 
 // Epilogue: 8 warps; warp w reads TMEM lane quadrant (w & 3) and the 16-column blocks j with (j & 1) == (w >> 2).
@@ -296,14 +306,17 @@ inline size_t tc_dw_i8_smem_bytes(const TcDwArgsI8 &a) {
            (size_t)a.Kpad * a.N + (size_t)a.Rmax * 4 + 128;
 }
 
-template <int NT>
+// WREG (C >= 64): the stencil's work item is 8 channels (half of a 16-byte group); a thread owns ONE half for all its rows, so
+// its 72 folded depthwise weights + 8 biases live in registers (with the weights in shared memory the 16-byte weight reads
+// of the 8 groups of a warp are 4-way bank conflicted and the kernel is shared-memory-wavefront bound).  Same arithmetic.
+template <int NT, bool WREG>
 __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwArgsI8 a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_b, bar_done;
     __shared__ uint32_t s_tmem;
     __shared__ int s_cpos[128];
     __shared__ float s_mult[256], s_bq[256];
-    __shared__ __align__(16) float s_dw[10 * 256];   // [tap][C] (input scale folded in), [9] = bias
+    __shared__ __align__(16) float s_dw[WREG ? 4 : 10 * 64];   // !WREG: [tap][C] (input scale folded in), [9] = bias (C < 64)
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int G = a.C >> 4;
@@ -337,7 +350,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
     if (warp == 1) tc::tmem_alloc<NT>(&s_tmem);
     pdl_trigger();
     if (tid < a.N) { s_mult[tid] = a.mult[blockIdx.y * a.N + tid]; s_bq[tid] = a.bq[blockIdx.y * a.N + tid]; }
-    for (int i = tid; i < 10 * a.C; i += TC_THREADS) s_dw[i] = i < 9 * a.C ? a.dw_w[i] : a.dw_b[i - 9 * a.C];
+    const int H8 = a.C >> 3, h_own = tid % H8;          // WREG: this thread's 8-channel half
+    float wreg[WREG ? 10 : 1][8];
+    if (WREG) {
+#pragma unroll
+        for (int t = 0; t < (WREG ? 10 : 1); t++) {
+            const float *src = (t < 9 ? a.dw_w + t * a.C : a.dw_b) + h_own * 8;
+            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(src)), w1 = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+            wreg[t][0] = w0.x; wreg[t][1] = w0.y; wreg[t][2] = w0.z; wreg[t][3] = w0.w;
+            wreg[t][4] = w1.x; wreg[t][5] = w1.y; wreg[t][6] = w1.z; wreg[t][7] = w1.w;
+        }
+    } else {
+        for (int i = tid; i < 10 * a.C; i += TC_THREADS) s_dw[i] = i < 9 * a.C ? a.dw_w[i] : a.dw_b[i - 9 * a.C];
+    }
     {
         const int lane = tid & 31;
         const int prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;
@@ -368,7 +393,29 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
     cp_async_wait_all();
     __syncthreads();
     // ---- depthwise stencil (FP32 on the int8 input; the input scale lives in the weights) -> int8 A operand ----
-    if (g_own < G) {
+    if (WREG) {
+        for (int r = tid / H8; r < a.rows; r += TC_THREADS / H8) {
+            const int cp = s_cpos[r];
+            if (cp < 0) continue;
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = wreg[WREG ? 9 : 0][i];
+            const unsigned char *base = sS + cp * pix + h_own * 8;
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                const int shift = (t / 3 - 1) * a.Wp + (t % 3 - 1);
+                float f[8];
+                tc::unpack8(*reinterpret_cast<const uint2 *>(base + shift * pix), f);
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] = __fadd_rn(acc[i], __fmul_rn(f[i], wreg[WREG ? t : 0][i]));     // no FMA, see below
+            }
+            int q[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) q[i] = tc::q8(__fmul_rn(fmaxf(acc[i], 0.f), a.inv_mid));
+            *reinterpret_cast<uint2 *>(sA + (size_t)(h_own >> 1) * lbo_a + (size_t)r * 16 + (h_own & 1) * 8) =
+                make_uint2(tc::pack4(q[0], q[1], q[2], q[3]), tc::pack4(q[4], q[5], q[6], q[7]));
+        }
+    } else if (g_own < G) {
         const int c0 = g_own * 16;
         for (int r = tid / GA; r < a.rows; r += TC_THREADS / GA) {
             const int cp = s_cpos[r];

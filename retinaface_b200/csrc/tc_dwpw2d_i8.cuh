@@ -36,19 +36,6 @@ inline size_t tc_dw2d_i8_smem_bytes(const TcDw2dArgsI8 &a) {
     return (size_t)a.PH * a.PW * a.C + (size_t)(a.Kpad / 16) * a.lbo_a + (size_t)a.Kpad * a.N + 128 + 16;
 }
 
-namespace tc {
-__device__ __forceinline__ void unpack8(const uint2 &v, float f[8]) {
-    const uint32_t w[2] = {v.x, v.y};
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        f[4 * i + 0] = (float)(int8_t)(w[i] & 0xff);
-        f[4 * i + 1] = (float)(int8_t)((w[i] >> 8) & 0xff);
-        f[4 * i + 2] = (float)(int8_t)((w[i] >> 16) & 0xff);
-        f[4 * i + 3] = (float)(int8_t)(w[i] >> 24);
-    }
-}
-}  // namespace tc
-
 template <int NT>
 __global__ void __launch_bounds__(TC_THREADS, 3) k_tc_dwpw_2d_i8(const TcDw2dArgsI8 a) {
     extern __shared__ __align__(128) unsigned char smem[];
