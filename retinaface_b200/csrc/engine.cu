@@ -365,6 +365,33 @@ DwGeom dw_geometry(int C, int N, int IH, int IW, int S) {
     return {0, 0, 0};
 }
 
+// Constants of the tensor-core stem (stem_tc.cuh) as one blob: conv0's folded FP32 weights as two FP16 pieces (hi + lo), the
+// pointwise B image, then the FP32 constants.  w0: [27][8] (k = (tap*3 + c_bgr), out channel), wd: [9][8], wp: [8][16].
+static std::vector<__half> make_stem_blob(const std::vector<float> &w0, const std::vector<float> &b0, const std::vector<float> &wd,
+                                          const std::vector<float> &bd, const std::vector<float> &wp, const std::vector<float> &bp) {
+    std::vector<__half> b0img(2 * 4 * 16 * 8, __float2half(0.f)), b1img(2 * 16 * 8, __float2half(0.f));
+    for (int k = 0; k < 27; k++)
+        for (int o = 0; o < 8; o++) {
+            const float wv = w0[k * 8 + o];
+            const __half hi = __float2half(wv);
+            b0img[((k / 8) * 16 + o) * 8 + (k % 8)] = hi;                                            // w = hi + lo
+            b0img[((4 + k / 8) * 16 + o) * 8 + (k % 8)] = __float2half(wv - __half2float(hi));
+        }
+    for (int c = 0; c < 8; c++)
+        for (int o = 0; o < 16; o++) b1img[(0 * 16 + o) * 8 + c] = __float2half(wp[c * 16 + o]);
+    std::vector<__half> blob(STEM_CONST_BYTES / 2, __float2half(0.f));
+    memcpy(blob.data(), b0img.data(), STEM_B0_BYTES);
+    memcpy(reinterpret_cast<unsigned char *>(blob.data()) + STEM_B0_BYTES, b1img.data(), STEM_B1_BYTES);
+    std::vector<float> fl;
+    fl.insert(fl.end(), b0.begin(), b0.begin() + 8);
+    fl.insert(fl.end(), wd.begin(), wd.begin() + 72);
+    fl.insert(fl.end(), bd.begin(), bd.begin() + 8);
+    fl.insert(fl.end(), bp.begin(), bp.begin() + 16);
+    fl.insert(fl.end(), wp.begin(), wp.begin() + 128);
+    memcpy(reinterpret_cast<unsigned char *>(blob.data()) + STEM_B0_BYTES + STEM_B1_BYTES, fl.data(), STEM_F_FLOATS * 4);
+    return blob;
+}
+
 template <typename T>
 void build_plan(rf_handle h) {
     Builder B{h, h->cfg.net_h, h->cfg.net_w};
@@ -394,29 +421,7 @@ void build_plan(rf_handle h) {
                 for (int c = 0; c < 8; c++) wp[c * 16 + o] = pw.w[(size_t)o * 8 + c];
             size_t ow0 = B.add_weights(w0), ob0 = B.add_weights(c0.b), owd = B.add_weights(wd), obd = B.add_weights(dw.b),
                    owp = B.add_weights(wp), obp = B.add_weights(pw.b);
-            // tensor-core operand images: B0 [4][16][8] (k = (tap*3 + c_bgr), n = out channel), B1 [2][16][8]
-            std::vector<__half> b0img(2 * 4 * 16 * 8, __float2half(0.f)), b1img(2 * 16 * 8, __float2half(0.f));
-            for (int k = 0; k < 27; k++)
-                for (int o = 0; o < 8; o++) {
-                    const float wv = w0[k * 8 + o];
-                    const __half hi = __float2half(wv);
-                    b0img[((k / 8) * 16 + o) * 8 + (k % 8)] = hi;                                            // w = hi + lo
-                    b0img[((4 + k / 8) * 16 + o) * 8 + (k % 8)] = __float2half(wv - __half2float(hi));
-                }
-            for (int c = 0; c < 8; c++)
-                for (int o = 0; o < 16; o++) b1img[(0 * 16 + o) * 8 + c] = __float2half(wp[c * 16 + o]);
-            // one blob for the tensor-core stem (stem_tc.cuh): B images, then the FP32 constants
-            std::vector<__half> blob(STEM_CONST_BYTES / 2, __float2half(0.f));
-            memcpy(blob.data(), b0img.data(), STEM_B0_BYTES);
-            memcpy(reinterpret_cast<unsigned char *>(blob.data()) + STEM_B0_BYTES, b1img.data(), STEM_B1_BYTES);
-            {
-                std::vector<float> fl;
-                fl.insert(fl.end(), c0.b.begin(), c0.b.begin() + 8);
-                fl.insert(fl.end(), wd.begin(), wd.end());
-                fl.insert(fl.end(), dw.b.begin(), dw.b.begin() + 8);
-                fl.insert(fl.end(), pw.b.begin(), pw.b.begin() + 16);
-                memcpy(reinterpret_cast<unsigned char *>(blob.data()) + STEM_B0_BYTES + STEM_B1_BYTES, fl.data(), STEM_F_FLOATS * 4);
-            }
+            std::vector<__half> blob = make_stem_blob(w0, c0.b, wd, dw.b, wp, pw.b);
             size_t oblob = B.add_weights_h(blob);
             const bool simt_stem = (h->cfg.flags & (RF_FLAG_SIMT_STEM | RF_FLAG_NO_TENSORCORE)) != 0;
             cur = B.tensor("mobilenet0_relu2_fwd", cur_h, cur_w, 16);
@@ -433,7 +438,7 @@ void build_plan(rf_handle h) {
                     launch_k(k_stem<__half>, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), sw, n, H, W, 1.0f);
                 } else {
                     StemTcArgs a{reinterpret_cast<const unsigned char *>(h->d_weights_h + oblob)};
-                    launch_k(k_stem_tc, dim3((unsigned)((W / 2 + 15) / 16), (unsigned)((H / 2 + 15) / 16), (unsigned)n), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), a, n, H, W);
+                    launch_k(k_stem_tc<__half>, dim3((unsigned)((W / 2 + 15) / 16), (unsigned)((H / 2 + 15) / 16), (unsigned)n), dim3(256), 0, st, (const PostParams *)h->d_params, (__half *)T_(out), a, n, H, W, 1.0f);
                 }
             };
             B.step(std::move(s));
@@ -905,10 +910,21 @@ void build_plan_i8(rf_handle h) {
         s.out = {out};
         s.flops_per_img = 2.0 * cur_h * cur_w * (8 * 27 + 8 * 9 + 8 * 16);
         s.bytes_per_img = (double)H * W * 3 + (double)cur_h * cur_w * 16;
+        // conv0 on tensor cores, depthwise + pointwise in FP32 on CUDA cores (stem_tc.cuh, OutT = int8_t); RF_FLAG_SIMT_STEM:
+        // all three layers on CUDA cores (k_stem)
+        const bool simt_stem = (h->cfg.flags & (RF_FLAG_SIMT_STEM | RF_FLAG_NO_TENSORCORE)) != 0;
+        size_t oblob = B.add_weights_h(make_stem_blob(w0, c0.b, wd, dw.b, wp, pw.b));
+        if (!simt_stem) s.name = "tc_stem_conv0+dw1+pw2_u8_to_16ch_i8";
         s.launch = [=](int n, cudaStream_t st) {
-            StemWeights sw{Wd(ow0), Wd(ob0), Wd(owd), Wd(obd), Wd(owp), Wd(obp)};
-            const int tiles = ((H / 2 + 15) / 16) * ((W / 2 + 15) / 16);
-            launch_k(k_stem<int8_t>, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, Q_(out), sw, n, H, W, inv);
+            if (simt_stem) {
+                StemWeights sw{Wd(ow0), Wd(ob0), Wd(owd), Wd(obd), Wd(owp), Wd(obp)};
+                const int tiles = ((H / 2 + 15) / 16) * ((W / 2 + 15) / 16);
+                launch_k(k_stem<int8_t>, dim3((unsigned)(tiles * n)), dim3(256), 0, st, (const PostParams *)h->d_params, Q_(out), sw, n, H, W, inv);
+            } else {
+                StemTcArgs a{reinterpret_cast<const unsigned char *>(h->d_weights_h + oblob)};
+                launch_k(k_stem_tc<int8_t>, dim3((unsigned)((W / 2 + 15) / 16), (unsigned)((H / 2 + 15) / 16), (unsigned)n), dim3(256), 0, st,
+                         (const PostParams *)h->d_params, Q_(out), a, n, H, W, inv);
+            }
         };
         B.step(std::move(s));
     }

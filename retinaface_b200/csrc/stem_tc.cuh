@@ -25,8 +25,9 @@ namespace rf {
 //   [0, 2048)     conv0 B images [hi, lo][4 K-groups][16 n][8] halfs, k = (ky*3+kx)*3 + c_bgr, n >= 8 and k >= 27 zero;
 //                 w = hi + lo (two FP16 pieces, 22 significant bits) accumulated by two MMAs per K step
 //   [2048, 2560)  conv2 B image [2 K-groups][16 n][8] halfs, k = channel (k >= 8 zero)
-//   [2560, 2976)  floats: conv0 bias [8], depthwise weights [9][8], depthwise bias [8], conv2 bias [16]
-constexpr int STEM_B0_BYTES = 2 * 4 * 16 * 8 * 2, STEM_B1_BYTES = 2 * 16 * 8 * 2, STEM_F_FLOATS = 8 + 72 + 8 + 16;
+//   [2560, 3488)  floats: conv0 bias [8], depthwise weights [9][8], depthwise bias [8], conv2 bias [16], conv2 weights [8][16]
+//                 (FP32, for the INT8 engine's CUDA-core pointwise stage)
+constexpr int STEM_B0_BYTES = 2 * 4 * 16 * 8 * 2, STEM_B1_BYTES = 2 * 16 * 8 * 2, STEM_F_FLOATS = 8 + 72 + 8 + 16 + 128;
 constexpr int STEM_CONST_BYTES = STEM_B0_BYTES + STEM_B1_BYTES + STEM_F_FLOATS * 4;
 static_assert(STEM_CONST_BYTES % 16 == 0, "bulk copy size");
 struct StemTcArgs {
@@ -36,8 +37,14 @@ struct StemTcArgs {
 constexpr int STEM_LBO0 = 384 * 16 + 16;    // A0: 3 tiles x 128 rows
 constexpr int STEM_LBO1 = 256 * 16 + 16;    // A1: 2 tiles x 128 rows
 
-__global__ void __launch_bounds__(256, 6) k_stem_tc(const PostParams *__restrict__ run, __half *__restrict__ out, StemTcArgs w,
-                                                    int n, int H, int W) {
+// OutT = __half: the FP16 engine (both dense layers on tensor cores).  OutT = int8_t: the INT8 engine -- conv0 on tensor cores
+// (hi/lo weights: FP32-grade), depthwise AND pointwise in FP32 on CUDA cores with the operation order of k_stem
+// (kernels_simt.cuh), output quantised with out_inv_scale: rounding the depthwise output to FP16 for a pointwise GEMM would
+// break the <= 1 LSB agreement with the integer oracle's FP32 stem (oracle/mnet_int8.py).
+template <typename OutT>
+__global__ void __launch_bounds__(256, 6) k_stem_tc(const PostParams *__restrict__ run, OutT *__restrict__ out, StemTcArgs w,
+                                                    int n, int H, int W, float out_inv_scale) {
+    constexpr bool I8 = sizeof(OutT) == 1;
     __shared__ __align__(16) uint8_t s_in[37][116];
     __shared__ __align__(128) unsigned char s_a0[4 * STEM_LBO0];
     __shared__ __align__(128) unsigned char s_const[STEM_CONST_BYTES];
@@ -206,12 +213,54 @@ __global__ void __launch_bounds__(256, 6) k_stem_tc(const PostParams *__restrict
                 }
             }
         const int row = ty * 16 + tx;
-        const __half2 h00 = __floats2half2_rn(fmaxf(d0[0], 0.f), fmaxf(d0[1], 0.f)), h01 = __floats2half2_rn(fmaxf(d0[2], 0.f), fmaxf(d0[3], 0.f));
-        const __half2 h10 = __floats2half2_rn(fmaxf(d1[0], 0.f), fmaxf(d1[1], 0.f)), h11 = __floats2half2_rn(fmaxf(d1[2], 0.f), fmaxf(d1[3], 0.f));
-        *reinterpret_cast<uint2 *>(s_a1 + row * 16 + plane * 8) = make_uint2(*reinterpret_cast<const uint32_t *>(&h00), *reinterpret_cast<const uint32_t *>(&h01));
-        *reinterpret_cast<uint2 *>(s_a1 + (row + 16) * 16 + plane * 8) = make_uint2(*reinterpret_cast<const uint32_t *>(&h10), *reinterpret_cast<const uint32_t *>(&h11));
-        *reinterpret_cast<uint4 *>(s_a1 + STEM_LBO1 + tid * 16) = make_uint4(0, 0, 0, 0);      // K padding (channels 8..15)
+        if constexpr (I8) {
+            // FP32 depthwise output -> shared [plane][pixel][4] (the pointwise operand's place, unused here)
+            float (*s_dwo)[256][4] = reinterpret_cast<float (*)[256][4]>(s_a1);
+            *reinterpret_cast<float4 *>(&s_dwo[plane][row][0]) = make_float4(fmaxf(d0[0], 0.f), fmaxf(d0[1], 0.f), fmaxf(d0[2], 0.f), fmaxf(d0[3], 0.f));
+            *reinterpret_cast<float4 *>(&s_dwo[plane][row + 16][0]) = make_float4(fmaxf(d1[0], 0.f), fmaxf(d1[1], 0.f), fmaxf(d1[2], 0.f), fmaxf(d1[3], 0.f));
+        } else {
+            const __half2 h00 = __floats2half2_rn(fmaxf(d0[0], 0.f), fmaxf(d0[1], 0.f)), h01 = __floats2half2_rn(fmaxf(d0[2], 0.f), fmaxf(d0[3], 0.f));
+            const __half2 h10 = __floats2half2_rn(fmaxf(d1[0], 0.f), fmaxf(d1[1], 0.f)), h11 = __floats2half2_rn(fmaxf(d1[2], 0.f), fmaxf(d1[3], 0.f));
+            *reinterpret_cast<uint2 *>(s_a1 + row * 16 + plane * 8) = make_uint2(*reinterpret_cast<const uint32_t *>(&h00), *reinterpret_cast<const uint32_t *>(&h01));
+            *reinterpret_cast<uint2 *>(s_a1 + (row + 16) * 16 + plane * 8) = make_uint2(*reinterpret_cast<const uint32_t *>(&h10), *reinterpret_cast<const uint32_t *>(&h11));
+            *reinterpret_cast<uint4 *>(s_a1 + STEM_LBO1 + tid * 16) = make_uint4(0, 0, 0, 0);      // K padding (channels 8..15)
+        }
     }
+    if constexpr (I8) {
+        // ---- 6'. pointwise 8 -> 16 in FP32 (k_stem's operation order), ReLU, quantise, one 16-byte store per pixel -------
+        __syncthreads();
+        const float (*s_dwo)[256][4] = reinterpret_cast<const float (*)[256][4]>(s_a1);
+        const float *s_wp = s_bias2 + 16;
+        const int oy = oy0 + (tid >> 4), ox = ox0 + (tid & 15);
+        if (oy < OH && ox < OW) {
+            const float4 da = *reinterpret_cast<const float4 *>(&s_dwo[0][tid][0]), db = *reinterpret_cast<const float4 *>(&s_dwo[1][tid][0]);
+            const float d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) o[j] = s_bias2[j];
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(&s_wp[c * 16 + j4 * 4]);
+                    o[j4 * 4 + 0] = fmaf(d[c], wv.x, o[j4 * 4 + 0]); o[j4 * 4 + 1] = fmaf(d[c], wv.y, o[j4 * 4 + 1]);
+                    o[j4 * 4 + 2] = fmaf(d[c], wv.z, o[j4 * 4 + 2]); o[j4 * 4 + 3] = fmaf(d[c], wv.w, o[j4 * 4 + 3]);
+                }
+            uint32_t pk[4];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    int q = __float2int_rn(__fmul_rn(fmaxf(o[j4 * 4 + k], 0.f), out_inv_scale));
+                    q = max(-127, min(127, q));
+                    word |= (uint32_t)(q & 0xff) << (8 * k);
+                }
+                pk[j4] = word;
+            }
+            *reinterpret_cast<uint4 *>(out + (((size_t)b * OH + oy) * OW + ox) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    } else {
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -244,10 +293,11 @@ __global__ void __launch_bounds__(256, 6) k_stem_tc(const PostParams *__restrict
             Vec8<__half> v0, v1;
             v0.from_float(f);
             v1.from_float(f + 8);
-            __half *dst = out + (((size_t)b * OH + oy) * OW + ox) * 16;
+            __half *dst = reinterpret_cast<__half *>(out) + (((size_t)b * OH + oy) * OW + ox) * 16;
             v0.store(dst);
             v1.store(dst + 8);
         }
+    }
     }
     tc::tc_fence_before();
     __syncthreads();
