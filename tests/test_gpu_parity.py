@@ -207,8 +207,9 @@ def test_preprocess_letterbox_bit_exact(golden_image):
 @pytest.mark.parametrize("model", ["mnet25", "mnet-deconv-0517"])
 def test_fp16_forward_and_detect(model, golden_image, post_oracle):
     """FP16 path (configs[1]): head tensors vs golden FP32 heads within FP16 tolerance
-    (cls_prob abs 5e-3, deltas abs 2e-2), detections on the golden image: same faces as the
-    FP32 golden ones, boxes within 0.5 px, scores within 5e-3; and internal consistency
+    (cls_prob abs 5e-3, deltas abs 2e-2 over ALL anchors; observed 3e-3 / 1e-2), detections on the golden image:
+    same faces as the FP32 golden ones, scores within 1e-3 (north_star's FP16 tolerance; observed 1.2e-4) and
+    boxes / landmarks within 0.1 px (observed 0.02 px); and internal consistency
     (its own heads -> oracle post-process == its own detect) bit-exact in selection."""
     from retinaface_b200 import RF_PREC_FP16
     eng = _engine(model, 448, 448, RF_PREC_FP16, max_batch=8)
@@ -223,8 +224,8 @@ def test_fp16_forward_and_detect(model, golden_image, post_oracle):
         dets = np.load(os.path.join(GOLDEN, f"dets_{model}_448x448.npz"))["faces_thr0.9"]
         faces, idx = eng.detect_batch(list(batch), 0.9, 0.4, want_index=True)
         assert faces[0].shape == dets.shape
-        assert np.abs(faces[0][:, 0] - dets[:, 0]).max() < 5e-3
-        assert np.abs(faces[0][:, 1:] - dets[:, 1:]).max() < 0.5
+        assert np.abs(faces[0][:, 0] - dets[:, 0]).max() < 1e-3
+        assert np.abs(faces[0][:, 1:] - dets[:, 1:]).max() < 0.1
         for i in range(8):
             ref = post_oracle.postprocess([x[i] for x in heads], 448, 448, 0.9, 0.4)
             _compare_dets(faces[i], idx[i], ref, f"fp16 img {i}")
