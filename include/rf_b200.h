@@ -79,9 +79,9 @@ typedef struct rf_config {
 } rf_config;
 
 #define RF_FLAG_NO_GRAPH      0x1u  /* launch kernels directly instead of replaying a CUDA graph */
-#define RF_FLAG_NO_TENSORCORE 0x2u  /* FP16: use the SIMT kernels for GEMM-shaped layers too */
-#define RF_FLAG_DW_1D         0x8u  /* FP16: linear (1-D) tiles for every depthwise+pointwise layer, also on large maps */
-#define RF_FLAG_SIMT_STEM     0x4u  /* FP16: run the stem's dense layers on CUDA cores (FP32 conv0 weights) */
+#define RF_FLAG_NO_TENSORCORE 0x2u  /* FP16: use the SIMT kernels for GEMM-shaped layers too (implies RF_FLAG_SIMT_STEM) */
+#define RF_FLAG_SIMT_STEM     0x4u  /* FP16 / INT8: run all three layers of the stem on CUDA cores (FP32 conv0 weights) */
+#define RF_FLAG_DW_1D         0x8u  /* FP16 / INT8: linear (1-D) tiles for every depthwise+pointwise layer, also on large maps */
 
 typedef struct rf_handle_s *rf_handle;
 
