@@ -621,3 +621,32 @@ def test_pinned_arbitrary_size_images_take_the_direct_copy_path(golden_image):
             assert np.array_equal(a, b)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp16", "int8"])
+@pytest.mark.parametrize("hw", [(448, 448), (288, 416)])
+def test_2d_tile_kernels_equal_the_1d_ones_bit_for_bit(prec, hw, golden_image):
+    """k_tc_dwpw_2d / k_tc_dwpw_2d_i8 (large maps) against the linear-tile kernels they replace (RF_FLAG_DW_1D): same
+    arithmetic in the same order, so every activation downstream -- and the heads -- must be IDENTICAL, including the
+    partial tiles of a 104x72 map (416x288 input)."""
+    from retinaface_b200 import RF_PREC_FP16, RF_PREC_INT8, Engine
+    from retinaface_b200.capi import RF_FLAG_DW_1D
+    h, w = hw
+    model = "mnet-deconv-0517"
+    kw = dict(precision=RF_PREC_FP16) if prec == "fp16" else dict(precision=RF_PREC_INT8,
+                                                                  int8_table=os.path.join(GOLDEN, "weights", model + ".table.int8"))
+    inp = letterbox_bgr_u8(golden_image, h, w)
+    batch = np.stack([inp, s_noise_batch(1, h, w, seed=5)[0], np.roll(inp, 16, axis=1)])
+    a = Engine(caffemodel(model), h, w, max_batch=3, **kw)
+    b = Engine(caffemodel(model), h, w, max_batch=3, flags=RF_FLAG_DW_1D, **kw)
+    try:
+        a.debug_keep_all()
+        b.debug_keep_all()
+        ha, hb = a.forward_heads(batch), b.forward_heads(batch)
+        for name in ("mobilenet0_relu4_fwd", "mobilenet0_relu6_fwd", "mobilenet0_relu10_fwd"):
+            assert np.array_equal(a.debug_tensor(name, 3), b.debug_tensor(name, 3)), name
+        for k in range(9):
+            assert np.array_equal(ha[k], hb[k]), k
+    finally:
+        a.close()
+        b.close()
