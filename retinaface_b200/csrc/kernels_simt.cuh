@@ -431,7 +431,7 @@ namespace rf {
 // into the consumer's staging (tc_conv.cuh UPADD) would push that kernel beyond one wave of CTAs.
 //   uwh: [16 taps][C] FP16 weights.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fpn_merge_h2(const __half *__restrict__ lateral, const __half *__restrict__ up,
+static __global__ void __launch_bounds__(256) k_fpn_merge_h2(const __half *__restrict__ lateral, const __half *__restrict__ up,
                                                       __half *__restrict__ out, const __half *__restrict__ uwh, int n, int H, int W, int C) {
     pdl_trigger();
     const int cg = C >> 3, UH = H >> 1, UW = W >> 1;
@@ -477,7 +477,7 @@ namespace rf {
 
 // FPN merge, INT8 path (c1 level): out_q = rint(q_lat * (s_lat/s_out) + sum_taps q_up * (w * s_up/s_out)), one thread per
 // (pixel, 16 channels).  wq: [16 taps][C] floats.
-__global__ void __launch_bounds__(256) k_fpn_merge_i8(const int8_t *__restrict__ lateral, const int8_t *__restrict__ up, int8_t *__restrict__ out,
+static __global__ void __launch_bounds__(256) k_fpn_merge_i8(const int8_t *__restrict__ lateral, const int8_t *__restrict__ up, int8_t *__restrict__ out,
                                                       const float *__restrict__ wq, float lat_mul, int n, int H, int W, int C) {
     pdl_trigger();
     const int cg = C >> 4, UH = H >> 1, UW = W >> 1;

@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
     };
     const int lo = centre(m0) - a.Wp - 1;
     const int R = (int)(centre(mlast) + a.Wp + 1 - lo) + 1;
-    if (R > a.Rmax) __trap();            // host-side geometry (engine.cu dw_geometry) must bound every tile
+    if (R > a.Rmax) __trap();            // host-side geometry (plan_fp.cu dw_geometry) must bound every tile
 
     if (tid == 0) {
         tc::mbar_init(&bar_b, 1);
