@@ -1,21 +1,22 @@
-// stem_tc.cuh -- the network stem on tensor cores (FP16 path): mobilenet0_conv0 (3x3 s2, 3->8) + BN + ReLU,
-// conv1 (depthwise 3x3) + BN + ReLU, conv2 (pointwise 8->16) + BN + ReLU  (prototxt:11-141) in one kernel,
-// u8 BGR image in, FP16 NHWC [n][H/2][W/2][16] out.
+// stem_tc.cuh -- the network stem on tensor cores: mobilenet0_conv0 (3x3 s2, 3->8) + BN + ReLU, conv1 (depthwise 3x3) + BN +
+// ReLU, conv2 (pointwise 8->16) + BN + ReLU  (prototxt:11-141) in one kernel, u8 BGR image in, NHWC [n][H/2][W/2][16] out
+// (FP16 for the FP16 engine, int8 for the INT8 engine).
 //
-// The CUDA-core stem (kernels_simt.cuh k_stem) spends two thirds of its instructions on the 216 + 128 FMAs per
-// pixel of the two dense layers.  Here both become tcgen05 GEMMs with the accumulator in TMEM and only the
-// depthwise stencil stays on CUDA cores:
-//   per CTA: a 16x16 tile of the H/2 x W/2 map (256 threads)
-//   1. stage the 37x37x3 u8 input patch (32-bit loads)
-//   2. im2col of conv0 for the 18x18 ring (324 rows, padded to 3 x 128) straight into the UMMA A operand: each
-//      thread converts the 27 u8 taps of one position to FP16 (exact) -- K = 27 padded to 32
-//   3. 3 tiles x 2 x tcgen05.mma (M=128, N=16 (8 used), K=16): conv0 for the whole ring
-//   4. TMEM -> registers: + bias, ReLU, zero outside the map (= the depthwise conv's padding) -> shared (FP32)
-//   5. depthwise 3x3 + ReLU per output pixel on CUDA cores -> FP16 -> A operand of the pointwise GEMM
-//   6. 2 tiles x tcgen05.mma (M=128, N=16, K=16 (8 used)): conv2
-//   7. TMEM -> registers: + bias, ReLU, FP16 pack, 2 x 16-byte stores per pixel
-// conv0's folded weights are rounded to FP16 here (the CUDA-core stem keeps them FP32): relative 2^-11 per weight,
-// the same order as the FP16 rounding of every activation tensor downstream.
+// The CUDA-core stem (kernels_simt.cuh k_stem) spends two thirds of its instructions on the 216 + 128 FMAs per pixel of the
+// two dense layers.  Here they become tcgen05 GEMMs with the accumulator in TMEM and the depthwise stencil stays on CUDA cores:
+//   per CTA: a 16x16 tile of the H/2 x W/2 map (256 threads, 32 KB of shared memory, 40 registers: 6 CTAs per SM)
+//   1. stage the 37x37x3 u8 input patch (32-bit loads, all of a warp's rows in flight before the first store)
+//   2. im2col of conv0 for the 18x18 ring (324 rows, padded to 3 x 128) straight into the UMMA A operand: each thread turns the
+//      27 u8 taps of one position into FP16 by byte permutes (0x6400 | b = 1024 + b, minus 1024: exact) -- K = 27 padded to 32
+//   3. 3 tiles x 2 K-steps x {hi, lo} tcgen05.mma (M=128, N=16 (8 used), K=16): conv0 for the whole ring, the folded FP32
+//      weights split into two FP16 pieces (22 significant bits: conv0's BN carries the input normalisation)
+//   4. TMEM -> registers: + bias, ReLU, zero outside the map (= the depthwise conv's padding) -> shared FP32, two 4-channel
+//      planes (16-byte stride between neighbouring positions: conflict-free 128-bit accesses)
+//   5. depthwise 3x3 + ReLU on CUDA cores, thread = (plane, column, pair of output rows): 12 loads feed 2 outputs
+//   FP16 engine:  6. -> A operand of the pointwise GEMM, 2 tiles x tcgen05.mma (M=128, N=16, K=16 (8 used)): conv2
+//                 7. TMEM -> registers: + bias, ReLU, FP16 pack, 2 x 16-byte stores per pixel
+//   INT8 engine:  6'. pointwise 8->16 in FP32 on CUDA cores (operation order of k_stem), ReLU, quantise, one 16-byte store per
+//                 pixel -- within 1 LSB of the integer oracle's FP32 stem, which an FP16-rounded GEMM operand would not be
 #pragma once
 #include "tc_conv.cuh"
 
