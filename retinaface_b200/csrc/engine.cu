@@ -154,6 +154,8 @@ void destroy(rf_handle h) {
     cudaFree(h->pb_merge.flag_scratch); cudaFree(h->pb_merge.out_dets); cudaFree(h->pb_merge.out_counts); cudaFree(h->pb_merge.out_total_kept);
     cudaFree(h->d_weights); cudaFree(h->d_weights_h); cudaFree(h->d_weights_q); cudaFree(h->d_input); cudaFree(h->d_raw);
     for (auto p : h->d_blobs) cudaFree(p);
+    h->copy_pool.reset();
+    for (auto e : h->raw_ev) if (e) cudaEventDestroy(e);
     cudaFreeHost(h->h_input); cudaFreeHost(h->h_raw); cudaFreeHost(h->h_dets); cudaFreeHost(h->h_counts);
     for (auto &sl : h->slots) {
         cudaFree(sl.d_in); cudaFreeHost(sl.h_in); cudaFreeHost(sl.h_dets); cudaFreeHost(sl.h_counts);
@@ -292,7 +294,8 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
         CK(cudaHostAlloc(&h->h_input, in_bytes, cudaHostAllocDefault));
         h->raw_bytes = (size_t)h->cfg.max_image_w * h->cfg.max_image_h * 3;
         CK(cudaMalloc(&h->d_raw, h->raw_bytes));
-        CK(cudaHostAlloc(&h->h_raw, h->raw_bytes, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&h->h_raw, 2 * h->raw_bytes, cudaHostAllocDefault));
+        for (auto &e : h->raw_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaHostAlloc(&h->h_dets, sizeof(rf_det) * (size_t)Bm * h->cfg.max_faces, cudaHostAllocDefault));
         CK(cudaHostAlloc(&h->h_counts, sizeof(int) * 2 * Bm, cudaHostAllocDefault));
         // ---- per-context resources ----
@@ -423,9 +426,10 @@ static int fetch_results(rf_handle h, int n, rf_face *out_faces, int *out_counts
 }
 
 // One caller image of arbitrary size -> d_raw (packed rows) on the handle's stream.  Pinned sources (cudaHostAlloc /
-// cudaHostRegister) are copied straight from the caller's memory, row stride and all, with no host synchronisation: the
-// stream orders the copy behind the letter-box kernel that still reads the previous image.  Pageable sources go through
-// the library's single pinned buffer (one host memcpy per image: ~10x the cost of the DMA itself).
+// cudaHostRegister) are copied straight from the caller's memory, row stride and all.  Pageable sources are staged through
+// two pinned buffers: a row-band parallel host copy (host_copy.h) into one buffer overlaps the DMA out of the other; the
+// only host wait is for the DMA that last read the buffer about to be overwritten.  In both cases the stream orders the
+// copy into d_raw behind the letter-box kernel that still reads the previous image.
 static void upload_raw(rf_handle h, const uint8_t *src, int width, int height, int row_stride) {
     cudaPointerAttributes at{};
     const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
@@ -434,9 +438,13 @@ static void upload_raw(rf_handle h, const uint8_t *src, int width, int height, i
         return;
     }
     cudaGetLastError();
-    CK(cudaStreamSynchronize(h->stream));  // h_raw is single-buffered
-    for (int y = 0; y < height; y++) memcpy(h->h_raw + (size_t)y * width * 3, src + (size_t)y * row_stride, (size_t)width * 3);
-    CK(cudaMemcpyAsync(h->d_raw, h->h_raw, (size_t)width * height * 3, cudaMemcpyHostToDevice, h->stream));
+    if (!h->copy_pool) h->copy_pool.reset(new HostCopyPool((int)std::min(3u, std::max(1u, std::thread::hardware_concurrency()) - 1u)));
+    const int slot = (int)(h->raw_seq++ & 1u);
+    uint8_t *buf = h->h_raw + (size_t)slot * h->raw_bytes;
+    CK(cudaEventSynchronize(h->raw_ev[slot]));      // (returns at once for an event never recorded)
+    h->copy_pool->copy_rows(buf, src, (size_t)width * 3, (size_t)row_stride, height);
+    CK(cudaMemcpyAsync(h->d_raw, buf, (size_t)width * height * 3, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->raw_ev[slot], h->stream));
 }
 
 int rf_detect_batch(rf_handle h, const uint8_t *const *imgs, const int *widths, const int *heights, const int *row_strides,

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_copy.h"
 #include "model.h"
 #include "postproc.cuh"
 
@@ -97,8 +98,11 @@ struct rf_handle_s {
     uint8_t *h_input = nullptr;       // pinned mirror
     PostBuffers pb_merge{};           // rf_detect_views: candidates of all views of one image (lazily allocated)
     uint8_t *d_raw = nullptr;         // one raw caller image (max_image) for the letterbox kernel
-    uint8_t *h_raw = nullptr;         // pinned
+    uint8_t *h_raw = nullptr;         // pinned, TWO buffers of raw_bytes: staging of pageable caller images (upload_raw)
     size_t raw_bytes = 0;
+    cudaEvent_t raw_ev[2] = {nullptr, nullptr};   // H2D out of staging buffer i has completed
+    unsigned raw_seq = 0;
+    std::unique_ptr<HostCopyPool> copy_pool;      // row-band parallel host copy into the staging buffers (lazily created)
     PostParams *d_params = nullptr, *h_params = nullptr;
     PostBuffers pb{};
     LevelDesc lv[3];
