@@ -79,15 +79,44 @@ def make_batches(wl, count, rank):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons, sampled during the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region: NVML every 2 ms when pynvml can open the device (the
+    timed region of the default run is ~30 ms), else one `nvidia-smi` query per 100 ms.  Rows have nvidia-smi's layout."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.stop_ev = gpu, [], threading.Event()
+        self.source = "nvidia-smi"
+
+    def _nvml_loop(self) -> bool:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            dev = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = nv.nvmlDeviceGetMaxClockInfo(dev, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+            nv.nvmlDeviceGetClockInfo(dev, nv.NVML_CLOCK_SM)          # probe once before committing to this source
+        except Exception:
+            return False
+        self.source = "nvml"
+        while not self.stop_ev.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(dev, nv.NVML_CLOCK_SM)
+                r = int(get_reasons(dev))
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.002)
+        return True
 
     def run(self):
+        if self._nvml_loop():
+            return
         while not self.stop_ev.is_set():
             try:
                 o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
@@ -106,7 +135,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(self.rows))
+                    samples=len(self.rows), source=self.source)
 
 
 # ------------------------------------------------------------------------------------------------
