@@ -82,6 +82,8 @@ typedef struct rf_config {
 #define RF_FLAG_NO_TENSORCORE 0x2u  /* FP16: use the SIMT kernels for GEMM-shaped layers too (implies RF_FLAG_SIMT_STEM) */
 #define RF_FLAG_SIMT_STEM     0x4u  /* FP16 / INT8: run all three layers of the stem on CUDA cores (FP32 conv0 weights) */
 #define RF_FLAG_DW_1D         0x8u  /* FP16 / INT8: linear (1-D) tiles for every depthwise+pointwise layer, also on large maps */
+#define RF_FLAG_LEGACY_TC     0x10u /* FP16: one round-1 tensor-core kernel per layer (pair) instead of the persistent tile chains
+                                       (tile_chain.cuh); the cross-check of the chains */
 
 typedef struct rf_handle_s *rf_handle;
 
@@ -195,6 +197,10 @@ int rf_profile_layers(rf_handle h, int n, int iters, char (*names)[64], float *m
 int rf_calibrate_int8(rf_handle h, const uint8_t *bgr_net_sized, int n_images, const char *out_table_path);
 /* Host-only: the threshold search of the calibrator on one histogram (returns the threshold in bins). */
 double rf_kl_threshold_bins(const unsigned *hist, int bins, int levels);
+
+/* Host-only (works without a GPU): the layer plan rf_create would build for `cfg`, one text line per kernel launch of a
+ * forward plus the geometry / shared-memory budget of every persistent tile chain.  Returns the launch count. */
+int rf_plan_describe(const rf_config *cfg, char *out, int cap);
 
 /* Debug / parity aids (not part of the drop-in surface): fetch a materialised activation by its
  * Caffe top name (e.g. "mobilenet0_relu10_fwd", "_plus0", "rf_c1_det_concat_relu") as NCHW

@@ -19,6 +19,7 @@ SOURCES = [
     ("engine.cu", []),
     ("plan_fp.cu", []),
     ("plan_i8.cu", []),
+    ("plan_tile.cu", []),
     ("postproc.cu", ["-fmad=false"]),
     ("preprocess.cu", ["-fmad=false"]),
     ("calibrate.cu", []),

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 RF_PREC_FP32, RF_PREC_FP16, RF_PREC_INT8 = 0, 1, 2
-RF_FLAG_NO_GRAPH, RF_FLAG_NO_TENSORCORE, RF_FLAG_SIMT_STEM, RF_FLAG_DW_1D = 0x1, 0x2, 0x4, 0x8
+RF_FLAG_NO_GRAPH, RF_FLAG_NO_TENSORCORE, RF_FLAG_SIMT_STEM, RF_FLAG_DW_1D, RF_FLAG_LEGACY_TC = 0x1, 0x2, 0x4, 0x8, 0x10
 FACE_FLOATS = 15
 PIPELINE_DEPTH = 6   # RF_PIPELINE_DEPTH
 
@@ -21,7 +21,7 @@ EXPORTS = [
     "rf_pinned_input", "rf_device_input", "rf_detect_batch", "rf_submit_batch", "rf_collect_batch", "rf_detect_batch_device", "rf_forward_heads",
     "rf_postprocess", "rf_preprocess", "rf_get_net_size", "rf_num_anchors", "rf_stream", "rf_synchronize", "rf_fence", "rf_last_stream",
     "rf_launches_per_batch", "rf_profile_layers", "rf_debug_get_tensor", "rf_debug_keep_all", "rf_model_inspect", "rf_calibrate_int8", "rf_kl_threshold_bins",
-    "rf_detect_views",
+    "rf_detect_views", "rf_plan_describe",
 ]
 
 
@@ -115,6 +115,19 @@ def model_inspect(caffemodel: str, layer: str):
     if rc != 0:
         raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
     return w, b
+
+
+def plan_describe(caffemodel: str, net_h: int, net_w: int, precision: int = RF_PREC_FP16, max_batch: int = 8, flags: int = 0,
+                  int8_table: Optional[str] = None) -> str:
+    """The layer plan rf_create would build (host-only entry point: no GPU needed)."""
+    lib = load_library()
+    cfg = _Config(caffemodel.encode(), int8_table.encode() if int8_table else None, precision, net_w, net_h, max_batch, 0, 0, 0, 0, flags, 0)
+    buf = C.create_string_buffer(1 << 16)
+    lib.rf_plan_describe.argtypes = [C.POINTER(_Config), C.c_char_p, C.c_int]
+    rc = lib.rf_plan_describe(C.byref(cfg), buf, len(buf))
+    if rc < 0:
+        raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
+    return buf.value.decode()
 
 
 def kl_threshold_bins(hist: np.ndarray, levels: int = 128) -> float:

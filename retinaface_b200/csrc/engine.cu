@@ -33,6 +33,13 @@ void link_steps(rf_handle h) {
             }
         }
     }
+    // the forward ends on the main lane: side lanes whose last step nobody waits for (SSH chains with fused predictors)
+    // are joined explicitly at the end of run_steps
+    for (int l = 1; l < 3; l++) {
+        h->lane_last[l] = -1;
+        for (int i = 0; i < (int)st.size(); i++) if (st[i].lane == l) h->lane_last[l] = i;
+        if (h->lane_last[l] >= 0) st[h->lane_last[l]].signals = true;
+    }
 }
 
 // Liveness-based first-fit placement of activation tensors in one arena.  Steps on side lanes run
@@ -97,6 +104,9 @@ void run_steps(rf_handle h, int n, cudaStream_t s, bool use_lanes = true) {
         st.launch(n, cs);
         if (use_lanes && st.signals) CK(cudaEventRecord(h->step_event[i], cs));
     }
+    if (use_lanes)
+        for (int l = 1; l < 3; l++)
+            if (h->lane_last[l] >= 0) CK(cudaStreamWaitEvent(s, h->step_event[h->lane_last[l]], 0));
 }
 
 void forward_graph(rf_handle h, int n) {
@@ -144,7 +154,7 @@ void destroy(rf_handle h) {
         h->graphs.clear();
         cudaFree(h->arena); cudaFree(h->d_params); cudaFreeHost(h->h_params);
         cudaFree(h->pb.cand_keys); cudaFree(h->pb.cand_recs); cudaFree(h->pb.cand_count); cudaFree(h->pb.sort_scratch);
-        cudaFree(h->pb.flag_scratch); cudaFree(h->pb.out_dets); cudaFree(h->pb.out_counts); cudaFree(h->pb.out_total_kept);
+        cudaFree(h->pb.flag_scratch); cudaFree(h->pb.out_dets); cudaFree(h->pb.out_counts); cudaFree(h->pb.out_total_kept); cudaFree(h->pb.tile_done);
         for (auto e : h->step_event) if (e) cudaEventDestroy(e);
         for (int l = 1; l < 3; l++) if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
         if (h->fence) cudaEventDestroy(h->fence);
@@ -156,7 +166,7 @@ void destroy(rf_handle h) {
     for (auto p : h->d_blobs) cudaFree(p);
     h->copy_pool.reset();
     for (auto e : h->raw_ev) if (e) cudaEventDestroy(e);
-    cudaFreeHost(h->h_input); cudaFreeHost(h->h_raw); cudaFreeHost(h->h_dets); cudaFreeHost(h->h_counts);
+    cudaFreeHost(h->h_input); cudaFreeHost(h->h_raw); cudaFreeHost(h->h_dets); cudaFreeHost(h->h_counts); cudaFreeHost(h->tile_dbg);
     for (auto &sl : h->slots) {
         cudaFree(sl.d_in); cudaFreeHost(sl.h_in); cudaFreeHost(sl.h_dets); cudaFreeHost(sl.h_counts);
         if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
@@ -211,6 +221,15 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
     if (cfg->net_w <= 0 || cfg->net_h <= 0 || cfg->net_w % 32 || cfg->net_h % 32)
         return fail(nullptr, RF_ERR_INVALID_ARG, fmt("rf_create: net size %dx%d must be positive multiples of 32", cfg->net_w, cfg->net_h));
     if (cfg->max_batch <= 0 || cfg->max_batch > 4096) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_create: max_batch must be in [1, 4096]");
+    {
+        // The kernels index activations with 32-bit element offsets (and pack (image row) << 12 | column in the FPN merge):
+        // the largest tensor of a batch -- the stem output, (H/2) x (W/2) x 16 -- must stay below 2^31 elements.
+        const long long stem_elems = (long long)cfg->max_batch * (cfg->net_h / 2) * (cfg->net_w / 2) * 16;
+        const long long merge_rows = (long long)cfg->max_batch * (cfg->net_h / 8);
+        if (stem_elems > 0x7fffffffLL || merge_rows >= (1LL << 19) || cfg->net_w / 8 >= (1 << 12))
+            return fail(nullptr, RF_ERR_CAPACITY, fmt("rf_create: max_batch %d at %dx%d exceeds the 32-bit activation index range (largest tensor: %lld elements); "
+                                                      "use a smaller max_batch", cfg->max_batch, cfg->net_w, cfg->net_h, stem_elems));
+    }
     if (cfg->precision != RF_PREC_FP32 && cfg->precision != RF_PREC_FP16 && cfg->precision != RF_PREC_INT8)
         return fail(nullptr, RF_ERR_INVALID_ARG, "rf_create: unknown precision");
     if (cfg->precision == RF_PREC_INT8 && !cfg->int8_table_path)
@@ -276,6 +295,7 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
         if (h->use_tc) CK(tc_init());
         if (h->cfg.precision == RF_PREC_INT8) { CK(tc_init_i8()); build_plan_i8(h); }
         else if (h->cfg.precision == RF_PREC_FP32) build_plan<float>(h);
+        else if (h->use_tc && !(h->cfg.flags & RF_FLAG_LEGACY_TC)) { CK(tile_init()); build_plan_tiles(h); }
         else build_plan<__half>(h);
         link_steps(h);
         place_tensors(h, false);
@@ -298,6 +318,9 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
         for (auto &e : h->raw_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaHostAlloc(&h->h_dets, sizeof(rf_det) * (size_t)Bm * h->cfg.max_faces, cudaHostAllocDefault));
         CK(cudaHostAlloc(&h->h_counts, sizeof(int) * 2 * Bm, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&h->tile_dbg, 64, cudaHostAllocMapped));
+        memset(h->tile_dbg, 0, 64);
+        CK(cudaHostGetDevicePointer(&h->tile_dbg_dev, h->tile_dbg, 0));
         // ---- per-context resources ----
         h->nctx = h->cfg.streams <= 0 ? 4 : std::min(h->cfg.streams, 4);
         h->saved.resize(h->nctx);
@@ -324,6 +347,8 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
             CK(cudaMalloc(&pb.out_counts, sizeof(int) * Bm));
             CK(cudaMalloc(&pb.out_total_kept, sizeof(int) * Bm));
             CK(cudaMemset(pb.out_counts, 0, sizeof(int) * Bm));
+            CK(cudaMalloc(&pb.tile_done, sizeof(int) * Bm));
+            CK(cudaMemset(pb.tile_done, 0, sizeof(int) * Bm));
         }
         switch_ctx(h, 0);
         for (int l = 0; l < 3; l++) {
@@ -333,6 +358,8 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
         CK(cudaDeviceSynchronize());
     } catch (const CudaFail &f) {
         return fail_cuda(nullptr, f);
+    } catch (const PlanFail &f) {
+        return fail(nullptr, f.status, "rf_create: " + f.msg);
     }
     *out = H.release();
     return RF_OK;
@@ -868,6 +895,40 @@ int rf_model_inspect(const char *caffemodel_path, const char *layer, float *w, i
     return RF_OK;
 }
 
+// Host-only (works without a GPU): builds the layer plan rf_create would build for `cfg` and writes one line per kernel
+// launch of a forward (and, for tile chains, their geometry and shared-memory / TMEM budget) into `out`.
+int rf_plan_describe(const rf_config *cfg, char *out, int cap) {
+    if (!cfg || !cfg->caffemodel_path || !out || cap <= 0) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_plan_describe: bad arguments");
+    if (cfg->net_w <= 0 || cfg->net_h <= 0 || cfg->net_w % 32 || cfg->net_h % 32 || cfg->max_batch <= 0)
+        return fail(nullptr, RF_ERR_INVALID_ARG, "rf_plan_describe: bad network size / batch");
+    std::unique_ptr<rf_handle_s> H(new rf_handle_s);
+    rf_handle h = H.get();
+    h->cfg = *cfg;
+    if (h->cfg.max_faces <= 0) h->cfg.max_faces = 256;
+    h->elem = cfg->precision == RF_PREC_FP32 ? 4 : (cfg->precision == RF_PREC_FP16 ? 2 : 1);
+    std::vector<RawLayer> layers;
+    std::string err;
+    bool io = false;
+    if (!read_caffemodel(cfg->caffemodel_path, layers, err, io)) return fail(nullptr, io ? RF_ERR_IO : RF_ERR_MODEL, err);
+    if (!build_mnet_model(layers, h->model, err)) return fail(nullptr, RF_ERR_MODEL, err);
+    if (cfg->int8_table_path && !read_int8_table(cfg->int8_table_path, h->int8_scales, err)) return fail(nullptr, RF_ERR_IO, err);
+    try {
+        h->use_tc = cfg->precision == RF_PREC_INT8 || (cfg->precision == RF_PREC_FP16 && !(cfg->flags & RF_FLAG_NO_TENSORCORE));
+        if (cfg->precision == RF_PREC_INT8) build_plan_i8(h);
+        else if (cfg->precision == RF_PREC_FP32) build_plan<float>(h);
+        else if (h->use_tc && !(cfg->flags & RF_FLAG_LEGACY_TC)) build_plan_tiles(h);
+        else build_plan<__half>(h);
+        link_steps(h);
+        place_tensors(h, false);
+    } catch (const CudaFail &f) { return fail_cuda(nullptr, f); }
+    catch (const PlanFail &f) { return fail(nullptr, f.status, f.msg); }
+    std::string text = fmt("%d launches per forward, activation arena %zu bytes per batch of %d\n", (int)h->steps.size(), h->arena_bytes, cfg->max_batch);
+    for (auto &st : h->steps) text += fmt("step lane %d: %s\n", st.lane, st.name.c_str());
+    text += describe_chains(h);
+    snprintf(out, (size_t)cap, "%s", text.c_str());
+    return (int)h->steps.size();
+}
+
 int rf_profile_layers(rf_handle h, int n, int iters, char (*names)[64], float *ms, double *bytes, double *flops, int cap) {
     int rc = check_n(h, n);
     if (rc) return rc;
@@ -916,6 +977,10 @@ int rf_profile_layers(rf_handle h, int n, int iters, char (*names)[64], float *m
             cnt++;
         }
         CK(cudaGetLastError());
+        // single steps were launched out of their forward: leave the last-block / candidate counters as a forward expects them
+        CK(cudaMemsetAsync(h->pb.tile_done, 0, sizeof(int) * h->cfg.max_batch, h->stream));
+        CK(cudaMemsetAsync(h->pb.cand_count, 0, sizeof(int) * h->cfg.max_batch, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
     } catch (const CudaFail &f) { return fail_cuda(h, f); }
     return cnt;
 }

@@ -27,9 +27,12 @@ using namespace rf;
 
 namespace rf_eng {
 
+struct TileChain;                 // plan_tile.cu
 std::string &create_error();      // thread-local text of the last failed rf_create (engine.cu)
 
 struct CudaFail { cudaError_t e; const char *what; const char *file; int line; };
+// a plan-time failure that is not a CUDA error: carries the rf_status and the full message to rf_create / the caller
+struct PlanFail { int status; std::string msg; };
 #define CK(call)                                                        \
     do {                                                                \
         cudaError_t _e = (call);                                        \
@@ -80,7 +83,13 @@ struct rf_handle_s {
     std::vector<TensorInfo> tensors;
     std::map<std::string, int> tensor_by_name;
     std::vector<Step> steps;
-    int head_step = -1;
+    int head_step = -1, nms_step = -1;
+    std::vector<std::shared_ptr<TileChain>> chains;   // tile-chain launches of the FP16 plan (plan_tile.cu)
+    unsigned tile_mask = 0;                           // which parts of the FP16 plan run as tile chains (RF_TILE_MASK)
+    int lane_last[3] = {-1, -1, -1};                  // last step of each side lane (joined at the end of the forward)
+    int tile_expected = 0;                            // tiles per image over the three SSH chains (last-block NMS)
+    std::vector<float> tile_bias_tmp;                 // plan-time scratch
+    unsigned *tile_dbg = nullptr, *tile_dbg_dev = nullptr;   // host-mapped word a timed-out hand-off of a tile chain reports into
     unsigned char *arena = nullptr;
     size_t arena_bytes = 0;
 
@@ -183,7 +192,10 @@ inline int fail(rf_handle h, int code, const std::string &msg) {
     return code;
 }
 inline int fail_cuda(rf_handle h, const CudaFail &f) {
-    return fail(h, RF_ERR_CUDA, fmt("%s failed: %s (%s:%d)", f.what, cudaGetErrorString(f.e), f.file, f.line));
+    std::string extra;
+    if (h && h->tile_dbg && h->tile_dbg[0])
+        extra = fmt(" [tile chain: CTA %u timed out waiting at tile_chain.cuh:%u]", h->tile_dbg[0] >> 20, h->tile_dbg[0] & 0xfffffu);
+    return fail(h, RF_ERR_CUDA, fmt("%s failed: %s (%s:%d)%s", f.what, cudaGetErrorString(f.e), f.file, f.line, extra.c_str()));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -229,6 +241,18 @@ void build_plan(rf_handle h);               // T = float (RF_PREC_FP32) | __half
 cudaError_t tc_init();
 std::vector<__half> make_stem_blob(const std::vector<float> &w0, const std::vector<float> &b0, const std::vector<float> &wd,
                                    const std::vector<float> &bd, const std::vector<float> &wp, const std::vector<float> &bp);
+int plan_stem_tc(Builder &B);
+int plan_pair_legacy(Builder &B, int i, int tin, int ih, int iw);
+void plan_conv_legacy(Builder &B, const std::string &sname, std::vector<const FoldedConv *> cs, int tin, int ih, int iw, int t0, int ld0,
+                      int off0, int n0, int relu0, int t1, int ld1, int off1, int relu1, int lane = 0, int tup = -1, int up_which = 0);
+int plan_fpn_merge_h2(Builder &B, const std::string &name, int tlat, int tup, int fh, int fw, int which);
+template <typename T>
+void plan_heads_and_nms(Builder &B, bool with_heads, bool with_nms);
+std::vector<__half> pack_tc_weights(const std::vector<const FoldedConv *> &cs, std::vector<float> &bias, int &Kpad, int nsplit = 1);
+// ---- exported by plan_tile.cu ---------------------------------------------------------------------------------------
+void build_plan_tiles(rf_handle h);         // RF_PREC_FP16 with tensor cores: tile chains (tile_chain.cuh) + round-1 kernels where no chain fits
+cudaError_t tile_init();
+std::string describe_chains(rf_handle h);
 // ---- exported by plan_i8.cu -----------------------------------------------------------------------------------------
 void build_plan_i8(rf_handle h);
 cudaError_t tc_init_i8();

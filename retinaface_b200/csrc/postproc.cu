@@ -16,63 +16,13 @@
 // rounding (__fmul_rn/__fadd_rn: no FMA contraction; the file is also built with -fmad=false),
 // and the `0.5 * (x - 1.0)` sub-expressions run in double like the reference's C++ does.
 // Ties in score (std::sort leaves them unspecified) are broken by emission order.
-#include "postproc.cuh"
+#include "postproc_dev.cuh"
 
 namespace rf {
 
 namespace {
 
 constexpr int NMS_THREADS = 512;
-constexpr int NMS_SMEM_CAP = 1024;  // candidates sorted / suppressed entirely in (static) shared memory
-constexpr int NMS_RANK_MAX = 256;   // up to here a one-pass rank sort replaces the bitonic ladder
-
-__device__ __forceinline__ unsigned long long make_key(float score, int emit) {
-    unsigned u = __float_as_uint(score);
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving float -> uint
-    return ((unsigned long long)(~u) << 32) | (unsigned)emit;  // ascending key == score desc, emit asc
-}
-
-// One anchor: RetinaFace.cpp:695-721 (+ :127-154 anchor, :378-398, :179-199, :418-432).
-__device__ __forceinline__ void decode_one(float conf, const float reg[4], const float lmk[10],
-                                           const LevelDesc &lv, int num, int ih, int iw, int net_w, int net_h,
-                                           int emit, rf_det &d) {
-    // anchors_plane: base + (iw*stride, ih*stride)   (int -> float conversions are exact here)
-    const float sw = (float)(iw * lv.stride), sh = (float)(ih * lv.stride);
-    const float ax1 = __fadd_rn(lv.base[4 * num + 0], sw), ay1 = __fadd_rn(lv.base[4 * num + 1], sh);
-    const float ax2 = __fadd_rn(lv.base[4 * num + 2], sw), ay2 = __fadd_rn(lv.base[4 * num + 3], sh);
-    const float width = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f);
-    const float height = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
-    const float ctr_x = (float)((double)ax1 + 0.5 * ((double)width - 1.0));
-    const float ctr_y = (float)((double)ay1 + 0.5 * ((double)height - 1.0));
-    const float pcx = __fadd_rn(__fmul_rn(reg[0], width), ctr_x);
-    const float pcy = __fadd_rn(__fmul_rn(reg[1], height), ctr_y);
-    const float pw = __fmul_rn((float)exp((double)reg[2]), width);
-    const float ph = __fmul_rn((float)exp((double)reg[3]), height);
-    float x1 = (float)((double)pcx - 0.5 * ((double)pw - 1.0));
-    float y1 = (float)((double)pcy - 0.5 * ((double)ph - 1.0));
-    float x2 = (float)((double)pcx + 0.5 * ((double)pw - 1.0));
-    float y2 = (float)((double)pcy + 0.5 * ((double)ph - 1.0));
-    // clip_boxes (single): x1,y1 only lower-clamped, x2,y2 only upper-clamped
-    if (x1 < 0) x1 = 0;
-    if (y1 < 0) y1 = 0;
-    if (x2 > (float)(net_w - 1)) x2 = (float)(net_w - 1);
-    if (y2 > (float)(net_h - 1)) y2 = (float)(net_h - 1);
-    d.face.score = conf;
-    d.face.x1 = x1; d.face.y1 = y1; d.face.x2 = x2; d.face.y2 = y2;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        d.face.lx[k] = __fadd_rn(__fmul_rn(lmk[2 * k], width), ctr_x);
-        d.face.ly[k] = __fadd_rn(__fmul_rn(lmk[2 * k + 1], height), ctr_y);
-    }
-    d.anchor_index = emit;
-}
-
-__device__ __forceinline__ void append_candidate(const PostBuffers &pb, int img, const rf_det &d) {
-    const size_t base = (size_t)img * pb.anchors_per_image;
-    pb.cand_recs[base + d.anchor_index] = d;
-    int slot = atomicAdd(&pb.cand_count[img], 1);
-    if (slot < pb.anchors_per_image) pb.cand_keys[base + slot] = make_key(d.face.score, d.anchor_index);
-}
 
 struct HeadLaunch {
     const void *feat[3];
@@ -134,13 +84,7 @@ __global__ void __launch_bounds__(128) k_head_decode(HeadLaunch L, int net_w, in
     // Softmax over the (N,2,2h,w) view (prototxt:1448-1483): anchor a pairs channel a (bg) with a+2 (face).
     float pf[2], pbg[2];
 #pragma unroll
-    for (int a = 0; a < 2; a++) {
-        float m = fmaxf(s[a], s[a + 2]);
-        float e0 = expf(__fsub_rn(s[a], m)), e1 = expf(__fsub_rn(s[a + 2], m));
-        float sum = __fadd_rn(e0, e1);
-        pbg[a] = __fdiv_rn(e0, sum);
-        pf[a] = __fdiv_rn(e1, sum);
-    }
+    for (int a = 0; a < 2; a++) softmax_pair(s[a], s[a + 2], pbg[a], pf[a]);
     const int ih = j / lv.w, iw = j % lv.w;
     if (WRITE_BLOBS) {
         float *cls = L.blobs[3 * l] + (size_t)img * 4 * hw;
@@ -204,120 +148,13 @@ __global__ void __launch_bounds__(256) k_blob_decode(BlobLaunch L, int net_w, in
     append_candidate(pb, img, d);
 }
 
-// IoU test of RetinaFace::nms (:470-487), operation by operation.
-__device__ __forceinline__ bool suppresses(const float4 s, float area1, const float4 b, float thr) {
-    float x = fmaxf(s.x, b.x), y = fmaxf(s.y, b.y);
-    float w = __fadd_rn(__fsub_rn(fminf(s.z, b.z), x), 1.0f);
-    float h = __fadd_rn(__fsub_rn(fminf(s.w, b.w), y), 1.0f);
-    if (w <= 0 || h <= 0) return false;
-    float area2 = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
-    float inter = __fmul_rn(w, h);
-    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area1, area2), inter)) > thr;
-}
-
-// One CTA per image.  (1) sort the candidate keys (rank sort for <= 256 candidates -- one pass, no
-// log^2 barrier ladder; bitonic above), (2) greedy suppression rounds: the next unsuppressed candidate is
-// kept, then all threads test the remaining ones against it -- the same O(n * kept) work as the reference,
-// parallel inside a round, (3) gather kept records.  Up to NMS_SMEM_CAP candidates live entirely in static
-// shared memory; beyond that (stress inputs) keys / flags use the global scratch of PostBuffers.
+// One CTA per image: sort + greedy NMS (postproc_dev.cuh nms_image).
 __global__ void __launch_bounds__(NMS_THREADS) k_nms(const PostParams *__restrict__ params, PostBuffers pb) {
     extern __shared__ int s_kept[];                         // [max_faces]
-    __shared__ unsigned long long s_keys[NMS_SMEM_CAP];
-    __shared__ unsigned long long s_tmp[NMS_RANK_MAX];
-    __shared__ float4 s_box[NMS_SMEM_CAP];
-    __shared__ unsigned char s_flag[NMS_SMEM_CAP];
-    __shared__ int s_nkept;
-    const int img = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int A = pb.anchors_per_image;
+    __shared__ NmsSmem S;
     pdl_trigger();
     pdl_wait();
-    int n = pb.cand_count[img];
-    if (n > A) n = A;
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    const bool small = np2 <= NMS_SMEM_CAP;
-    unsigned long long *keys = small ? s_keys : pb.sort_scratch + (size_t)img * pb.anchors_pow2;
-    unsigned char *flag = small ? s_flag : pb.flag_scratch + (size_t)img * pb.anchors_pow2;
-    const unsigned long long *gkeys = pb.cand_keys + (size_t)img * A;
-    const rf_det *recs = pb.cand_recs + (size_t)img * A;
-    if (tid == 0) s_nkept = 0;
-
-    if (n <= NMS_RANK_MAX) {
-        // rank sort: keys are unique (the emission index is part of the key), so rank = #smaller keys
-        for (int i = tid; i < n; i += NMS_THREADS) { s_tmp[i] = gkeys[i]; s_flag[i] = 0; }
-        __syncthreads();
-        for (int i = tid; i < n; i += NMS_THREADS) {
-            const unsigned long long k = s_tmp[i];
-            int rank = 0;
-            for (int j = 0; j < n; j++) rank += s_tmp[j] < k;
-            s_keys[rank] = k;
-        }
-        __syncthreads();
-    } else {
-        for (int i = tid; i < np2; i += NMS_THREADS) {
-            keys[i] = i < n ? gkeys[i] : ~0ull;
-            flag[i] = 0;
-        }
-        __syncthreads();
-        for (int k = 2; k <= np2; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < np2; i += NMS_THREADS) {
-                    int ixj = i ^ j;
-                    if (ixj > i) {
-                        unsigned long long a = keys[i], b = keys[ixj];
-                        bool up = (i & k) == 0;
-                        if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
-                    }
-                }
-                __syncthreads();
-            }
-        }
-    }
-    if (small) {
-        for (int i = tid; i < n; i += NMS_THREADS) {
-            const rf_face &f = recs[(unsigned)(keys[i] & 0xffffffffu)].face;
-            s_box[i] = make_float4(f.x1, f.y1, f.x2, f.y2);
-        }
-        __syncthreads();
-    }
-    const float thr = params->nms_thr;
-    auto box_at = [&](int i) -> float4 {
-        if (small) return s_box[i];
-        const rf_face &f = recs[(unsigned)(keys[i] & 0xffffffffu)].face;
-        return make_float4(f.x1, f.y1, f.x2, f.y2);
-    };
-    int nkept = 0;  // thread 0's running count (mirrored to s_nkept at the end)
-    for (int i = 0; i < n; i++) {
-        if (flag[i]) continue;  // uniform: flags of position i are final once every earlier kept round has synchronised
-        const float4 s = box_at(i);
-        if (tid == 0) {
-            if (nkept < pb.max_faces) s_kept[nkept] = i;
-            nkept++;
-        }
-        const float area1 = __fmul_rn(__fadd_rn(__fsub_rn(s.z, s.x), 1.0f), __fadd_rn(__fsub_rn(s.w, s.y), 1.0f));
-        for (int j = i + 1 + tid; j < n; j += NMS_THREADS) {
-            if (!flag[j] && suppresses(s, area1, box_at(j), thr)) flag[j] = 1;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) s_nkept = nkept;
-    __syncthreads();
-    const int total = s_nkept;
-    const int kept = total < pb.max_faces ? total : pb.max_faces;
-    // gather: 16 floats per record, one thread per float
-    const float *src = reinterpret_cast<const float *>(recs);
-    float *dst = reinterpret_cast<float *>(pb.out_dets + (size_t)img * pb.max_faces);
-    for (int t = tid; t < kept * 16; t += NMS_THREADS) {
-        int k = t >> 4, w = t & 15;
-        unsigned e = (unsigned)(keys[s_kept[k]] & 0xffffffffu);
-        dst[t] = src[(size_t)e * 16 + w];
-    }
-    if (tid == 0) {
-        pb.out_counts[img] = kept;
-        pb.out_total_kept[img] = total;
-        pb.cand_count[img] = 0;  // self-cleaning for the next launch
-    }
+    nms_image<NMS_THREADS, false>(blockIdx.x, threadIdx.x, params->nms_thr, pb, S, s_kept, [] { __syncthreads(); });
 }
 
 

@@ -14,6 +14,7 @@ struct PostBuffers {
     rf_det *out_dets;               // [B][max_faces]
     int *out_counts;                // [B]   kept (clamped to max_faces)
     int *out_total_kept;            // [B]   kept before clamping
+    int *tile_done;                 // [B]   tiles of the image finished (tile_chain.cuh last-block NMS; self-cleaning)
     int anchors_per_image;
     int anchors_pow2;
     int max_faces;
