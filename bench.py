@@ -17,6 +17,11 @@ Printed JSON (rank 0, one line):
              with one blocking rf_detect_batch per step (latency mode).
   roofline   dominant kernel: algorithmic bytes (layer-granular) / CUDA-event time of
              that kernel launched K times on the library's stream, vs MEASURED_PEAKS.json.
+  configs    the other BASELINE.json configurations measured in the same run (device-timed + end to end): batch 1 / 32,
+             configs[2] INT8 batch 32, configs[3] 1280x896; at --gpus 8: configs[4] INT8 batch 32 per GPU + all-gather.
+Timing: every number is the MEDIAN over blocks of K steps, blocks repeated until >= 0.3 s of timed work (a 2 ms window
+is not a measurement); `steps` stays K.  At N > 1 every step -- device-timed and end to end -- includes the exchange of
+the detection records (rf_detect_batch_device_allgather / rf_submit_batch_allgather: fused into the NMS kernel, comm.cu).
   cpu_baseline  the oracle (cv2.dnn FP32 forward of the same caffemodel through a generated prototxt +
              oracle/postproc.c) timed on the host cores on a bounded sample (rank 0, N=1 only).
 
@@ -52,7 +57,12 @@ WORKLOADS = {
     "mnet0517_fp16_b32_448": dict(model="mnet-deconv-0517", precision="fp16", batch=32, h=448, w=448),
     # configs[3]: large input / many-anchor NMS stress
     "mnet25_fp16_b8_1280x896": dict(model="mnet25", precision="fp16", batch=8, h=896, w=1280),
+    # configs[4] per GPU (B=256 over 8 GPUs): the reference ships no mnet25 table -> mnet-deconv-0517 + its TensorRT table
+    "mnet0517_int8_b32_448_per_gpu": dict(model="mnet-deconv-0517", precision="int8", batch=32, h=448, w=448),
 }
+EXTRA_1GPU = ["mnet25_fp16_b1_448", "mnet25_fp16_b32_448", "mnet0517_int8_b32_448", "mnet25_fp16_b8_1280x896"]
+EXTRA_NGPU = ["mnet0517_int8_b32_448_per_gpu"]
+MIN_TIMED_S = 0.3
 DEFAULT_WORKLOAD = "mnet25_fp16_b8_448"
 SCORE_THR, NMS_THR = 0.9, 0.4  # main.cpp:43, RetinaFace.h:66
 
@@ -185,8 +195,8 @@ def best_cpu_threads(wl, batch):
     return best
 
 
-def cpu_measure(wl, batches, budget_s, min_steps=2):
-    threads = best_cpu_threads(wl, batches[0])
+def cpu_measure(wl, batches, budget_s, min_steps=2, threads=None):
+    threads = threads or best_cpu_threads(wl, batches[0])
     cpu = CpuPath(wl, threads)
     cpu.step(batches[0])  # warm-up
     t0 = time.perf_counter()
@@ -195,10 +205,11 @@ def cpu_measure(wl, batches, budget_s, min_steps=2):
         faces += cpu.step(batches[steps % len(batches)])
         steps += 1
     dt = time.perf_counter() - t0
+    B = batches[0].shape[0]
     return dict(value=faces / dt, unit="faces/s", cores=threads, kind="port",
-                sample=f"{steps} batches of {wl['batch']} images ({steps * wl['batch']} images, {dt:.1f} s): cv2.dnn FP32 forward "
+                sample=f"{steps} batches of {B} images ({steps * B} images, {dt:.1f} s): cv2.dnn FP32 forward "
                        f"of {wl['model']}.caffemodel + oracle/postproc.c decode/NMS, {threads} threads",
-                images_per_s=steps * wl["batch"] / dt), dt, steps
+                images_per_s=steps * B / dt, ms_per_batch=dt / steps * 1e3), dt, steps
 
 
 # ------------------------------------------------------------------------------------------------
@@ -229,6 +240,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="measure only --workload (skip the `configs` dict)")
     ap.add_argument("--streams", type=int, default=0, help="execution contexts of the engine (0 = library default 2)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -273,175 +285,222 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: the path has no CPU fallback")
     torch.cuda.set_device(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from retinaface_b200 import RF_PREC_FP16, RF_PREC_FP32, RF_PREC_INT8, Engine
-    prec = {"fp16": RF_PREC_FP16, "fp32": RF_PREC_FP32, "int8": RF_PREC_INT8}[wl["precision"]]
-    B, H, Wd = wl["batch"], wl["h"], wl["w"]
-    eng = Engine(os.path.join(GOLD, "weights", wl["model"] + ".caffemodel"), H, Wd, precision=prec, max_batch=B,
-                 max_faces=128, device=local, streams=args.streams,
-                 int8_table=os.path.join(GOLD, "weights", wl["model"] + ".table.int8") if prec == RF_PREC_INT8 else None)
-    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=local)
-    img_bytes = B * H * Wd * 3
+    from retinaface_b200.capi import PIPELINE_DEPTH as depth
+    from retinaface_b200.multigpu import init_comm
+    precs = {"fp16": RF_PREC_FP16, "fp32": RF_PREC_FP32, "int8": RF_PREC_INT8}
     l2_bytes = 126 * 2**20
-    ring = max(4, min(256, -(-2 * l2_bytes // img_bytes)))     # input ring > 2 x L2
-    host = make_batches(wl, ring, rank)
-    pinned = torch.from_numpy(host).pin_memory()
-    dev = pinned.to(f"cuda:{local}", non_blocking=False)       # device-resident inputs for `value`
-    faces = np.empty((B, eng.max_faces, 15), dtype=np.float32)
-    counts = np.zeros(B, dtype=np.int32)
-    pin_np = pinned.numpy()
-
-    def e2e_step(slot):
-        imgs = [pin_np[slot, i] for i in range(B)]
-        return eng.detect_batch(imgs, SCORE_THR, NMS_THR)
-
-    # faces per ring slot (deterministic; also the warm-up of both paths)
-    faces_per_slot = np.zeros(ring, dtype=np.int64)
-    for s in range(ring):
-        faces_per_slot[s] = sum(len(f) for f in e2e_step(s))
-    # all-gather buffer for N>1: the fixed-size per-image detection records
-
-    def dev_tensor(ptr, nbytes):
-        class _W:  # minimal __cuda_array_interface__ carrier
-            pass
-        w = _W()
-        w.__cuda_array_interface__ = dict(shape=(nbytes,), typestr="|u1", data=(ptr, False), version=2)
-        return torch.as_tensor(w, device=f"cuda:{local}")
-
-    eng.detect_device(B, SCORE_THR, NMS_THR, dev[0].data_ptr())
-    eng.synchronize()
-    views = {}      # (dets ptr) -> (det view, count view, external stream) of one execution context
-
-    def device_step(slot):
-        dptr, cptr = eng.detect_device(B, SCORE_THR, NMS_THR, dev[slot].data_ptr())
-        if world > 1:
-            # the one exchange of the path: all-gather of this step's fixed-size detection records,
-            # issued on the stream the step ran on (each execution context has its own output buffers)
-            if dptr not in views:
-                views[dptr] = (dev_tensor(dptr, B * eng.max_faces * 64), dev_tensor(cptr, B * 4),
-                               torch.cuda.ExternalStream(eng.last_stream_ptr(), device=local),
-                               torch.empty(world * B * eng.max_faces * 64, dtype=torch.uint8, device=f"cuda:{local}"),
-                               torch.empty(world * B * 4, dtype=torch.uint8, device=f"cuda:{local}"))
-            dv, cv, st, gd, gc = views[dptr]
-            with torch.cuda.stream(st):
-                dist.all_gather_into_tensor(gd, dv)
-                dist.all_gather_into_tensor(gc, cv)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-timed value ---------------------------------------------------------------
-    for i in range(W):
-        device_step(i % ring)
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for i in range(K):
-        device_step((W + i) % ring)
-    eng.fence()                     # stream (context 0) now follows the work queued on every context
-    ev1.record(stream)
-    barrier()
-    dev_ms = ev0.elapsed_time(ev1)
-    dev_faces = int(sum(faces_per_slot[(W + i) % ring] for i in range(K)))
+    def agree_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
-    # ---- end-to-end, blocking call: rf_detect_batch (host pinned in, host faces out), one batch at a time ----
-    for i in range(W):
-        e2e_step(i % ring)
-    barrier()
-    t0 = time.perf_counter()
-    blk_faces = 0
-    for i in range(K):
-        out = e2e_step((W + i) % ring)
-        blk_faces += sum(len(f) for f in out)
-    barrier()
-    blk_s = time.perf_counter() - t0
-    # ---- end-to-end, pipelined: rf_submit_batch / rf_collect_batch, 3 batches in flight; every step still
-    #      copies its own input H2D from pinned memory and reads its own faces back ---------------------------
-    fbuf = np.empty((B, eng.max_faces, 15), dtype=np.float32)
-    cbuf = np.zeros(B, dtype=np.int32)
+    def agree_sum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
 
-    from retinaface_b200.capi import PIPELINE_DEPTH as depth
+    def measure(name, K, min_s, full):
+        """One workload on this rank's GPU: device-timed and end-to-end numbers as medians over blocks of K steps."""
+        w = dict(WORKLOADS[name])
+        prec = precs[w["precision"]]
+        B, H, Wd = w["batch"], w["h"], w["w"]
+        eng = Engine(os.path.join(GOLD, "weights", w["model"] + ".caffemodel"), H, Wd, precision=prec, max_batch=B,
+                     max_faces=128, device=local, streams=args.streams,
+                     int8_table=os.path.join(GOLD, "weights", w["model"] + ".table.int8") if prec == RF_PREC_INT8 else None)
+        if world > 1:
+            init_comm(eng, dist, rank, world, local)
+        gather = world > 1
+        stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=local)
+        img_bytes = B * H * Wd * 3
+        ring = max(4, min(256, -(-2 * l2_bytes // img_bytes)))     # input ring > 2 x L2
+        host = make_batches(w, ring, rank)
+        pinned = torch.from_numpy(host).pin_memory()
+        dev = pinned.to(f"cuda:{local}", non_blocking=False)       # device-resident inputs for `value`
+        pin_np = pinned.numpy()
+        rows = world * B if gather else B
+        fbuf = np.empty((rows, eng.max_faces, 15), dtype=np.float32)
+        cbuf = np.zeros(rows, dtype=np.int32)
 
-    def pipelined(nsteps, first):
-        inflight, nfaces = [], 0
-        for i in range(nsteps):
-            if len(inflight) == depth:
+        def pipelined(nsteps, first):
+            inflight, nfaces = [], 0
+            for i in range(nsteps):
+                if len(inflight) == depth:
+                    _, c = eng.collect(inflight.pop(0), fbuf, cbuf)
+                    nfaces += int(c[rank * B:(rank + 1) * B].sum()) if gather else int(c.sum())
+                slot = (first + i) % ring
+                inflight.append(eng.submit([pin_np[slot, j] for j in range(B)], SCORE_THR, NMS_THR, allgather=gather))
+            while inflight:
                 _, c = eng.collect(inflight.pop(0), fbuf, cbuf)
-                nfaces += int(c.sum())
-            slot = (first + i) % ring
-            inflight.append(eng.submit([pin_np[slot, j] for j in range(B)], SCORE_THR, NMS_THR))
-        while inflight:
-            _, c = eng.collect(inflight.pop(0), fbuf, cbuf)
-            nfaces += int(c.sum())
-        return nfaces
+                nfaces += int(c[rank * B:(rank + 1) * B].sum()) if gather else int(c.sum())
+            return nfaces
 
-    pipelined(W, 0)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_faces = pipelined(K, W)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.summary()
+        # faces per ring slot (deterministic; the end-to-end path is also the warm-up of the engine)
+        faces_per_slot = np.zeros(ring, dtype=np.int64)
+        barrier()
+        for s in range(ring):
+            faces_per_slot[s] = pipelined(1, s)
+        barrier()
 
-    if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, float(dev_faces), float(e2e_faces), blk_s, float(blk_faces)], dtype=torch.float64,
-                         device=f"cuda:{local}")
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_s, blk_s = float(tmax[0]), float(tmax[1]), float(tmax[4])
-        dev_faces, e2e_faces, blk_faces = int(tsum[2]), int(tsum[3]), int(tsum[5])
+        def device_step(slot):
+            if gather:
+                eng.detect_device_allgather(B, SCORE_THR, NMS_THR, dev[slot].data_ptr())
+            else:
+                eng.detect_device(B, SCORE_THR, NMS_THR, dev[slot].data_ptr())
+
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pos = [0]
+
+        def dev_block():
+            barrier()
+            ev0.record(stream)
+            for _ in range(K):
+                device_step(pos[0] % ring)
+                pos[0] += 1
+            eng.fence()                     # stream (context 0) now follows the work queued on every context
+            ev1.record(stream)
+            barrier()
+            return ev0.elapsed_time(ev1)
+
+        def e2e_block():
+            barrier()
+            t0 = time.perf_counter()
+            pipelined(K, pos[0])
+            pos[0] += K
+            barrier()
+            return (time.perf_counter() - t0) * 1e3
+
+        def blk_block():
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                eng.detect_batch([pin_np[pos[0] % ring, j] for j in range(B)], SCORE_THR, NMS_THR)
+                pos[0] += 1
+            barrier()
+            return (time.perf_counter() - t0) * 1e3
+
+        def run_blocks(block, warm):
+            """warm-up, then blocks of K steps until >= min_s of timed work on every rank; median block time (max over ranks)."""
+            for _ in range(warm):
+                block()
+            first = agree_max(block())
+            nblk = int(min(400, max(3, -(-min_s * 1e3 // max(first, 1e-3)))))
+            nblk = int(agree_max(nblk))
+            times = [first] + [block() for _ in range(nblk - 1)]
+            times = [agree_max(t) for t in times] if world > 1 else times
+            return float(np.median(times)), len(times), float(np.sum(times)) * 1e-3
+
+        mean_faces = float(faces_per_slot.mean())          # per step on this rank (the ring is walked round and round)
+        faces_step = agree_sum(mean_faces)                 # whole job
+        for i in range(W):
+            device_step(i % ring)
+        barrier()
+        out = dict(workload=name, precision=w["precision"], batch_per_gpu=B, input=f"{Wd}x{H}", launches_per_step=eng.launches_per_batch(B))
+        clock = None
+        if full:
+            clock = ClockSampler(local)
+            clock.start()
+        d_ms, d_n, d_s = run_blocks(dev_block, 1)
+        out.update(ms_per_step=d_ms / K, value=faces_step * K / (d_ms * 1e-3), images_per_s=K * B * world / (d_ms * 1e-3), timed_blocks=d_n, timed_region_s=d_s)
+        e_ms, e_n, e_s = run_blocks(e2e_block, 1)
+        out["e2e"] = dict(value=faces_step * K / (e_ms * 1e-3), unit="faces/s", h2d_bytes_per_step=img_bytes,
+                          d2h_bytes_per_step=(world if gather else 1) * (B * 4 + B * eng.max_faces * 64) + (4 if gather else 0),
+                          images_per_s=K * B * world / (e_ms * 1e-3), ms_per_step=e_ms / K, timed_blocks=e_n, timed_region_s=e_s,
+                          timing=f"host wall clock, median over blocks of K rf_submit_batch{'_allgather' if gather else ''}/rf_collect steps, {depth} batches in flight"
+                                 + ("; every step's results are the records of ALL ranks, host-visible" if gather else ""))
+        if full and not gather:
+            b_ms, b_n, b_s = run_blocks(blk_block, 1)
+            out["e2e"]["blocking"] = dict(value=faces_step * K / (b_ms * 1e-3), ms_per_step=b_ms / K, images_per_s=K * B * world / (b_ms * 1e-3),
+                                          note="one blocking rf_detect_batch per step (latency mode)")
+        if clock is not None:
+            out["clocks"] = clock.summary()
+        if full and rank == 0:
+            out["_prof"] = eng.profile_layers(B, iters=max(10, min(K, 100)))
+        out["_ring"] = ring
+        out["_img_bytes"] = img_bytes
+        out["_max_faces"] = eng.max_faces
+        eng.close()
+        return out
+
+    main_res = measure(args.workload, K, MIN_TIMED_S, True)
+    extras = {}
+    if not args.no_extra_configs:
+        for name in (EXTRA_NGPU if world > 1 else EXTRA_1GPU):
+            if name == args.workload:
+                continue
+            try:
+                r = measure(name, K, 0.15, False)
+                extras[name] = {k: v for k, v in r.items() if not k.startswith("_")}
+            except Exception as e:                      # a secondary configuration must not take the headline line down
+                extras[name] = dict(error=str(e)[:300])
 
     line = None
     if rank == 0:
         pk = peaks()
-        value = dev_faces / (dev_ms * 1e-3)
+        prec = precs[wl["precision"]]
+        prof = main_res.pop("_prof")
+        ring, img_bytes, mfaces = main_res.pop("_ring"), main_res.pop("_img_bytes"), main_res.pop("_max_faces")
         # ---- roofline of the dominant kernel (direct launches, CUDA events on the library stream) ----
-        prof = eng.profile_layers(B, iters=max(10, min(K, 100)))
         tot = sum(p["ms"] for p in prof)
         top = max(prof, key=lambda p: p["ms"])
         ach_gbs = top["bytes"] / (top["ms"] * 1e-3) / 1e9
         ach_tf = top["flops"] / (top["ms"] * 1e-3) / 1e12
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):            # dram__bytes_read+write of the dominant kernel from the committed ncu --set full capture
+        traffic, l2b, limiter, tsrc = None, None, None, None
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tp):            # the committed ncu --set full capture of this kernel (not re-measured in this run)
             tj = json.load(open(tp))
             if tj.get("workload") == args.workload and tj.get("kernel") == top["name"]:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                l2b, limiter, tsrc = tj.get("l2_bytes"), tj.get("limiter"), "profiles/r02_traffic.json (ncu --set full capture; file-sourced, not measured in this run)"
         roof = dict(bound="hbm", kernel=top["name"], achieved=ach_gbs, peak=pk["hbm_gbs"], unit="GB/s", frac=ach_gbs / pk["hbm_gbs"],
-                    traffic=traffic, peak_source=pk["src"], kernel_ms=top["ms"], kernel_share_of_step=top["ms"] / tot,
-                    tensor_tflops=ach_tf, tensor_frac=ach_tf / pk["bf16_tflops"],
+                    traffic=traffic, traffic_source=tsrc, l2_bytes=l2b, limiter=limiter, peak_source=pk["src"], kernel_ms=top["ms"],
+                    kernel_share_of_step=top["ms"] / tot, tensor_tflops=ach_tf, tensor_frac=ach_tf / pk["bf16_tflops"],
                     step_algorithmic_gb=sum(p["bytes"] for p in prof) / 1e9, step_algorithmic_gflop=sum(p["flops"] for p in prof) / 1e9,
-                    step_sum_of_kernels_ms=tot)
-        line = dict(metric="faces/sec (end-to-end detect)", value=value, unit="faces/s", n_gpus=world, steps=K, warmup=W,
-                    ms_per_step=dev_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype={RF_PREC_FP16: "f16", RF_PREC_FP32: "f32", RF_PREC_INT8: "s8"}[prec], data="synthetic", config=dict(config, execution_contexts=args.streams or 4, l2_policy=f"input ring of {ring} batches = {ring * img_bytes / 2**20:.0f} MiB > 2x L2; activations reused in place"),
-                    images_per_s=K * B * world / (dev_ms * 1e-3), clocks=clocks,
-                    e2e=dict(value=e2e_faces / e2e_s, unit="faces/s", h2d_bytes_per_step=img_bytes,
-                             d2h_bytes_per_step=B * 4 + B * eng.max_faces * 64, images_per_s=K * B * world / e2e_s,
-                             ms_per_step=e2e_s / K * 1e3,
-                             timing=f"host wall clock around K rf_submit_batch/rf_collect_batch steps, {depth} batches in flight",
-                             blocking=dict(value=blk_faces / blk_s, ms_per_step=blk_s / K * 1e3, images_per_s=K * B * world / blk_s,
-                                           note="one blocking rf_detect_batch per step (latency mode)")),
-                    gpu_launches=K * eng.launches_per_batch(B), launches_per_step=eng.launches_per_batch(B), roofline=roof,
-                    layers=[dict(name=p["name"], us=round(p["ms"] * 1e3, 2)) for p in prof])
-    eng_close = eng.close
+                    step_sum_of_kernels_ms=tot,
+                    note="kernel time: back-to-back launches of that kernel alone (L2-warm); algorithmic bytes = its input + output tensors")
+        line = dict(metric="faces/sec (end-to-end detect)", value=main_res["value"], unit="faces/s", n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=main_res["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype={RF_PREC_FP16: "f16", RF_PREC_FP32: "f32", RF_PREC_INT8: "s8"}[prec], data="synthetic",
+                    config=dict(config, execution_contexts=args.streams or 4,
+                                l2_policy=f"input ring of {ring} batches = {ring * img_bytes / 2**20:.0f} MiB > 2x L2; activations reused in place",
+                                timing=f"median over {main_res['timed_blocks']} blocks of {K} steps ({main_res['timed_region_s']:.2f} s timed)",
+                                exchange=("detection records of every step stored into every rank's gather window by the NMS kernel (NVLink peer "
+                                          "stores, comm.cu); included in value and e2e") if world > 1 else "none (1 GPU)"),
+                    images_per_s=main_res["images_per_s"], clocks=main_res.get("clocks"),
+                    e2e=main_res["e2e"], gpu_launches=K * main_res["launches_per_step"], launches_per_step=main_res["launches_per_step"],
+                    roofline=roof, layers=[dict(name=p["name"], us=round(p["ms"] * 1e3, 2)) for p in prof], configs=extras)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, _, _ = cpu_measure(wl, host[:4], args.cpu_seconds)
+        host = make_batches(wl, 4, 0)
+        cb, _, _ = cpu_measure(wl, host, args.cpu_seconds)
+        one, _, _ = cpu_measure(wl, host, max(3.0, args.cpu_seconds / 3), threads=1)
+        w1 = dict(wl, batch=1)
+        single = make_batches(w1, 4, 0)
+        s_all, _, _ = cpu_measure(w1, single, max(3.0, args.cpu_seconds / 4), threads=cb["cores"])
+        s_one, _, _ = cpu_measure(w1, single, max(3.0, args.cpu_seconds / 4), threads=1)
+        cb["one_core"] = dict(value=one["value"], images_per_s=one["images_per_s"], ms_per_batch=one["ms_per_batch"], cores=1)
+        cb["single_image"] = dict(note="BASELINE.json configs[0]: one 448x448 image per call (mnet25 FP32, CPU only)",
+                                  all_cores=dict(value=s_all["value"], ms_per_image=s_all["ms_per_batch"], cores=s_all["cores"]),
+                                  one_core=dict(value=s_one["value"], ms_per_image=s_one["ms_per_batch"], cores=1))
+        cb["host"] = dict(nproc=os.cpu_count())
         line["cpu_baseline"] = cb
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
         emit(line)
-    eng_close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -139,6 +139,34 @@ int rf_collect_batch(rf_handle h, int ticket, rf_face *out_faces, int *out_count
 int rf_detect_batch_device(rf_handle h, const uint8_t *dev_bgr, int n, float score_threshold,
                            float nms_threshold, const rf_det **dev_dets, const int32_t **dev_counts);
 
+/* ---- Multi-GPU (the reference is single-GPU: `ctx_id`, RetinaFace.h:89, is never used) --------------------
+ * One process (handle) per GPU; the batch is sharded over the ranks, weights are replicated, and the ONLY exchange is an
+ * all-gather of the per-image detection records -- fused into the NMS kernel: the CTA that finishes an image stores its kept
+ * faces straight into the gather window of every rank (peer device memory over NVLink, mapped with CUDA IPC) and raises a
+ * flag there.  Set-up: every rank calls rf_comm_export (allocates its window, fills an opaque 128-byte blob), the caller
+ * all-gathers the blobs by any means (MPI, torch.distributed, a file ...), every rank calls rf_comm_init with all of them in
+ * rank order.  rf_comm_init_nccl does the blob exchange itself through NCCL (libnccl.so.2 is opened at run time; the id
+ * comes from rf_comm_nccl_unique_id on one rank and reaches the others by the caller's means).
+ * All ranks must issue the same sequence of *_allgather calls with the same n. */
+#define RF_COMM_BLOB_BYTES 128
+#define RF_COMM_MAX_WORLD_SIZE 16
+int rf_comm_export(rf_handle h, int rank, int world, void *blob);
+int rf_comm_init(rf_handle h, const void *blobs /* world x RF_COMM_BLOB_BYTES, rank order */);
+int rf_comm_nccl_unique_id(void *out128);
+int rf_comm_init_nccl(rf_handle h, const void *nccl_unique_id /* 128 bytes */, int rank, int world);
+int rf_comm_info(rf_handle h, int *rank, int *world);
+/* rf_detect_batch_device + exchange: asynchronous; *all_dets -> [world][max_batch][max_faces] rf_det and *all_counts ->
+ * [world][max_batch] int32 in this rank's gather window (rank r's image i at r * max_batch + i), complete -- every rank's
+ * records have landed -- in stream order on rf_last_stream(); valid until 20 further exchanges. */
+int rf_detect_batch_device_allgather(rf_handle h, const uint8_t *dev_bgr, int n, float score_threshold, float nms_threshold,
+                                     const rf_det **all_dets, const int32_t **all_counts);
+/* rf_submit_batch / rf_collect_batch + exchange: out_faces [world * max_batch][max_faces], out_counts [world * max_batch]
+ * (host), rank r's image i at r * max_batch + i.  rf_detect_batch_allgather = submit + collect (blocking). */
+int rf_submit_batch_allgather(rf_handle h, const uint8_t *const *bgr_images, int n, float score_threshold, float nms_threshold, int *ticket);
+int rf_collect_batch_allgather(rf_handle h, int ticket, rf_face *out_faces, int *out_counts, int32_t *out_anchor_index);
+int rf_detect_batch_allgather(rf_handle h, const uint8_t *const *bgr_images, int n, float score_threshold, float nms_threshold,
+                              rf_face *out_faces, int *out_counts, int32_t *out_anchor_index);
+
 /* Parity/debug: replaces TrtRetinaFaceNet::doInference + blob_by_name (trtretinafacenet.cpp:48-114).
  * Host network-sized images in, the 9 head blobs out in the reference's blob order
  * (trtretinafacenet.cpp:23-31), NCHW float32, each heads_out[k] sized n*C*h*w. */

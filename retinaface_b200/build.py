@@ -20,6 +20,7 @@ SOURCES = [
     ("plan_fp.cu", []),
     ("plan_i8.cu", []),
     ("plan_tile.cu", []),
+    ("comm.cu", []),
     ("postproc.cu", ["-fmad=false"]),
     ("preprocess.cu", ["-fmad=false"]),
     ("calibrate.cu", []),

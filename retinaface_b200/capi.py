@@ -22,7 +22,10 @@ EXPORTS = [
     "rf_postprocess", "rf_preprocess", "rf_get_net_size", "rf_num_anchors", "rf_stream", "rf_synchronize", "rf_fence", "rf_last_stream",
     "rf_launches_per_batch", "rf_profile_layers", "rf_debug_get_tensor", "rf_debug_keep_all", "rf_model_inspect", "rf_calibrate_int8", "rf_kl_threshold_bins",
     "rf_detect_views", "rf_plan_describe",
+    "rf_comm_export", "rf_comm_init", "rf_comm_nccl_unique_id", "rf_comm_init_nccl", "rf_comm_info", "rf_detect_batch_device_allgather",
+    "rf_submit_batch_allgather", "rf_collect_batch_allgather", "rf_detect_batch_allgather",
 ]
+COMM_BLOB_BYTES = 128
 
 
 class _View(C.Structure):       # rf_view
@@ -96,6 +99,15 @@ def load_library() -> C.CDLL:
     lib.rf_calibrate_int8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p]
     lib.rf_kl_threshold_bins.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.rf_kl_threshold_bins.restype = C.c_double
+    lib.rf_comm_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.rf_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rf_comm_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.rf_comm_init_nccl.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.rf_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.rf_detect_batch_device_allgather.argtypes = lib.rf_detect_batch_device.argtypes
+    lib.rf_submit_batch_allgather.argtypes = lib.rf_submit_batch.argtypes
+    lib.rf_collect_batch_allgather.argtypes = lib.rf_collect_batch.argtypes
+    lib.rf_detect_batch_allgather.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -128,6 +140,16 @@ def plan_describe(caffemodel: str, net_h: int, net_w: int, precision: int = RF_P
     if rc < 0:
         raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
     return buf.value.decode()
+
+
+def nccl_unique_id() -> bytes:
+    """A fresh ncclUniqueId (rank 0 creates it, the caller ships it to the other ranks) for Engine.comm_init_nccl."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.rf_comm_nccl_unique_id(buf)
+    if rc != 0:
+        raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
+    return buf.raw
 
 
 def kl_threshold_bins(hist: np.ndarray, levels: int = 128) -> float:
@@ -212,6 +234,9 @@ class Engine:
         n = len(images)
         keep = [np.ascontiguousarray(im, dtype=np.uint8) if not (im.flags.c_contiguous and im.dtype == np.uint8) else im
                 for im in images]
+        for im in keep:
+            if im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError(f"u8 BGR HWC images expected, got shape {im.shape}")
         ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in keep])
         ws = (C.c_int * n)(*[im.shape[1] for im in keep])
         hs = (C.c_int * n)(*[im.shape[0] for im in keep])
@@ -237,25 +262,57 @@ class Engine:
         self._check(self.lib.rf_detect_batch(self.h, ptrs, ws, hs, None, n, thr, nms_thr, faces.ctypes.data,
                                              counts.ctypes.data, None))
 
-    def submit(self, images: Sequence[np.ndarray], thr: float, nms_thr: float) -> int:
+    def _net_sized(self, images: Sequence[np.ndarray]):
+        """rf_submit_batch reads net_h * net_w * 3 bytes from every pointer: refuse anything else."""
+        for im in images:
+            if im.shape != (self.net_h, self.net_w, 3) or im.dtype != np.uint8 or not im.flags.c_contiguous:
+                raise ValueError(f"network-sized C-contiguous uint8 images of shape {(self.net_h, self.net_w, 3)} expected, got {im.shape} {im.dtype}")
+
+    def submit(self, images: Sequence[np.ndarray], thr: float, nms_thr: float, allgather: bool = False) -> int:
         """Pipelined path: queue one batch of network-sized images (H2D on the copy stream + forward + D2H);
-        returns a ticket for collect().  Up to PIPELINE_DEPTH batches in flight."""
+        returns a ticket for collect().  Up to PIPELINE_DEPTH batches in flight.  allgather: the multi-GPU exchange too."""
         n = len(images)
+        self._net_sized(images)
         ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in images])
         t = C.c_int()
-        self._check(self.lib.rf_submit_batch(self.h, ptrs, n, thr, nms_thr, C.byref(t)))
+        fn = self.lib.rf_submit_batch_allgather if allgather else self.lib.rf_submit_batch
+        self._check(fn(self.h, ptrs, n, thr, nms_thr, C.byref(t)))
         self._inflight = getattr(self, "_inflight", {})
-        self._inflight[t.value] = (n, images)      # keep the sources alive until collected
+        self._inflight[t.value] = (n, images, allgather)      # keep the sources alive until collected
         return t.value
 
     def collect(self, ticket: int, faces: Optional[np.ndarray] = None, counts: Optional[np.ndarray] = None):
-        n, _ = self._inflight.pop(ticket)
+        n, _, allgather = self._inflight.pop(ticket)
+        rows = self.comm_world * self.max_batch if allgather else n
         if faces is None:
-            faces = np.empty((n, self.max_faces, FACE_FLOATS), dtype=np.float32)
+            faces = np.empty((rows, self.max_faces, FACE_FLOATS), dtype=np.float32)
         if counts is None:
-            counts = np.zeros(n, dtype=np.int32)
-        self._check(self.lib.rf_collect_batch(self.h, ticket, faces.ctypes.data, counts.ctypes.data, None))
+            counts = np.zeros(rows, dtype=np.int32)
+        fn = self.lib.rf_collect_batch_allgather if allgather else self.lib.rf_collect_batch
+        self._check(fn(self.h, ticket, faces.ctypes.data, counts.ctypes.data, None))
         return faces, counts
+
+    # -- multi-GPU ---------------------------------------------------------------------------
+    comm_world = 1
+
+    def comm_export(self, rank: int, world: int) -> bytes:
+        blob = C.create_string_buffer(COMM_BLOB_BYTES)
+        self._check(self.lib.rf_comm_export(self.h, rank, world, blob))
+        return blob.raw
+
+    def comm_init(self, blobs: Sequence[bytes]):
+        raw = b"".join(blobs)
+        self._check(self.lib.rf_comm_init(self.h, raw))
+        self.comm_world = len(blobs)
+
+    def comm_init_nccl(self, unique_id: bytes, rank: int, world: int):
+        self._check(self.lib.rf_comm_init_nccl(self.h, unique_id, rank, world))
+        self.comm_world = world
+
+    def detect_device_allgather(self, n: int, thr: float, nms_thr: float, dev_ptr: int):
+        d, c = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.rf_detect_batch_device_allgather(self.h, dev_ptr, n, thr, nms_thr, C.byref(d), C.byref(c)))
+        return int(d.value), int(c.value)
 
     def detect_device(self, n: int, thr: float, nms_thr: float, dev_ptr: Optional[int] = None):
         """Asynchronous device-resident detect.  Returns (dets_ptr, counts_ptr) device addresses."""

@@ -81,6 +81,8 @@ struct PostParams {          // device-resident: a replayed CUDA graph picks up 
     float score_thr;
     float nms_thr;
     const uint8_t *input;    // [n][net_h][net_w][3] u8 BGR images of this run (library buffer or caller's)
+    unsigned comm_seq;       // multi-GPU exchange (comm.cu): sequence number of this step (0: no exchange) ...
+    unsigned comm_slot;      // ... and its slot in every rank's gather window
 };
 
 }  // namespace rf

@@ -133,11 +133,13 @@ void forward_graph(rf_handle h, int n) {
 
 // Run parameters travel through a small ring of pinned slots so that an asynchronous caller
 // (rf_detect_batch_device) can queue several runs without overwriting a copy still in flight.
-void set_params(rf_handle h, float thr, float nms, const uint8_t *input = nullptr) {
+void set_params(rf_handle h, float thr, float nms, const uint8_t *input = nullptr, unsigned comm_seq = 0) {
     PostParams *slot = h->h_params + (h->param_seq++ % rf_handle_s::kParamSlots);
     slot->score_thr = thr;
     slot->nms_thr = nms;
     slot->input = input ? input : h->d_input;
+    slot->comm_seq = comm_seq;
+    slot->comm_slot = comm_seq ? comm_seq % (unsigned)h->comm.ring : 0u;
     h->cur_thr = thr;
     h->cur_nms = nms;
     CK(cudaMemcpyAsync(h->d_params, slot, sizeof(PostParams), cudaMemcpyHostToDevice, h->stream));
@@ -147,6 +149,8 @@ void destroy(rf_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->saved.empty()) h->saved.resize(1);
+    for (int c = 0; c < (int)h->saved.size(); c++) { switch_ctx(h, c); if (h->stream) cudaStreamSynchronize(h->stream); }
+    comm_release(h);
     for (int c = 0; c < (int)h->saved.size(); c++) {
         switch_ctx(h, c);
         if (h->stream) cudaStreamSynchronize(h->stream);
@@ -336,7 +340,7 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
             CK(cudaMalloc(&h->d_params, sizeof(PostParams)));
             CK(cudaHostAlloc(&h->h_params, sizeof(PostParams) * rf_handle_s::kParamSlots, cudaHostAllocDefault));
             PostBuffers &pb = h->pb;
-            pb.anchors_per_image = A; pb.anchors_pow2 = ap2; pb.max_faces = h->cfg.max_faces;
+            pb.anchors_per_image = A; pb.anchors_pow2 = ap2; pb.max_faces = h->cfg.max_faces; pb.max_batch = Bm;
             CK(cudaMalloc(&pb.cand_keys, sizeof(unsigned long long) * (size_t)Bm * A));
             CK(cudaMalloc(&pb.cand_recs, sizeof(rf_det) * (size_t)Bm * A));
             CK(cudaMalloc(&pb.cand_count, sizeof(int) * Bm));
@@ -416,22 +420,41 @@ int rf_launches_per_batch(rf_handle h, int n) {
     return h ? (int)h->steps.size() : RF_ERR_INVALID_ARG;
 }
 
-int rf_detect_batch_device(rf_handle h, const uint8_t *dev_bgr, int n, float thr, float nms, const rf_det **dev_dets,
-                           const int32_t **dev_counts) {
+static int detect_device_impl(rf_handle h, const uint8_t *dev_bgr, int n, float thr, float nms, const rf_det **dev_dets, const int32_t **dev_counts,
+                              bool gather) {
     int rc = check_n(h, n);
     if (rc) return rc;
+    if (gather && (!h->comm.ready || n == 0)) return fail(h, RF_ERR_INVALID_ARG, "rf_detect_batch_device_allgather: call rf_comm_init first (and n > 0)");
     try {
         CK(cudaSetDevice(h->device));
         switch_ctx(h, (int)(h->next_dev_ctx++ % (unsigned)h->nctx));   // consecutive batches overlap on different contexts
         h->last_stream = h->stream;
         // the caller's device images are read in place (conv0 takes the pointer from the run parameters)
         if (h->param_seq && h->param_seq % rf_handle_s::kParamSlots == 0) CK(cudaStreamSynchronize(h->stream));
-        set_params(h, thr, nms, dev_bgr);
+        const unsigned seq = gather ? ++h->comm.seq : 0u;
+        set_params(h, thr, nms, dev_bgr, seq);
         if (n > 0) forward_graph(h, n);
+        if (gather) {
+            const unsigned slot = seq % (unsigned)h->comm.ring;
+            comm_wait(h, seq, slot, n, h->stream);
+            const size_t img0 = (size_t)slot * h->comm.world * h->cfg.max_batch;
+            if (dev_dets) *dev_dets = h->pb.comm.dets[h->comm.rank] + img0 * h->cfg.max_faces;
+            if (dev_counts) *dev_counts = h->pb.comm.counts[h->comm.rank] + img0;
+            return RF_OK;
+        }
     } catch (const CudaFail &f) { return fail_cuda(h, f); }
     if (dev_dets) *dev_dets = h->pb.out_dets;
     if (dev_counts) *dev_counts = h->pb.out_counts;
     return RF_OK;
+}
+
+int rf_detect_batch_device(rf_handle h, const uint8_t *dev_bgr, int n, float thr, float nms, const rf_det **dev_dets,
+                           const int32_t **dev_counts) {
+    return detect_device_impl(h, dev_bgr, n, thr, nms, dev_dets, dev_counts, false);
+}
+int rf_detect_batch_device_allgather(rf_handle h, const uint8_t *dev_bgr, int n, float thr, float nms, const rf_det **all_dets,
+                                     const int32_t **all_counts) {
+    return detect_device_impl(h, dev_bgr, n, thr, nms, all_dets, all_counts, true);
 }
 
 static int fetch_results(rf_handle h, int n, rf_face *out_faces, int *out_counts, int32_t *out_idx, int *out_ncand) {
@@ -548,10 +571,11 @@ static void ensure_slots(rf_handle h) {
     }
 }
 
-int rf_submit_batch(rf_handle h, const uint8_t *const *imgs, int n, float thr, float nms, int *ticket) {
+static int submit_impl(rf_handle h, const uint8_t *const *imgs, int n, float thr, float nms, int *ticket, bool gather) {
     int rc = check_n(h, n);
     if (rc) return rc;
     if (!imgs || !ticket || n == 0) return fail(h, RF_ERR_INVALID_ARG, "rf_submit_batch: NULL argument or empty batch");
+    if (gather && !h->comm.ready) return fail(h, RF_ERR_INVALID_ARG, "rf_submit_batch_allgather: call rf_comm_init first");
     const size_t img_bytes = (size_t)h->cfg.net_h * h->cfg.net_w * 3;
     try {
         CK(cudaSetDevice(h->device));
@@ -585,33 +609,90 @@ int rf_submit_batch(rf_handle h, const uint8_t *const *imgs, int n, float thr, f
         CK(cudaEventRecord(sl.ev_h2d, h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, sl.ev_h2d, 0));
         if (h->param_seq && h->param_seq % rf_handle_s::kParamSlots == 0) CK(cudaStreamSynchronize(h->stream));
-        set_params(h, thr, nms, sl.d_in);
+        const unsigned seq = gather ? ++h->comm.seq : 0u;
+        set_params(h, thr, nms, sl.d_in, seq);
         forward_graph(h, n);
-        CK(cudaMemcpyAsync(sl.h_counts, h->pb.out_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(sl.h_dets, h->pb.out_dets, sizeof(rf_det) * (size_t)n * h->cfg.max_faces, cudaMemcpyDeviceToHost, h->stream));
+        if (gather) {
+            // results of ALL ranks: wait for every rank's flags of this step, then read this rank's window slot
+            Comm::Slot &cs = h->comm.slots[h->submit_seq % RF_PIPELINE_DEPTH];
+            const size_t nimg = (size_t)h->comm.world * h->cfg.max_batch;
+            if (!cs.h_dets) {
+                CK(cudaHostAlloc(&cs.h_dets, sizeof(rf_det) * nimg * h->cfg.max_faces, cudaHostAllocDefault));
+                CK(cudaHostAlloc(&cs.h_counts, sizeof(int) * nimg, cudaHostAllocDefault));
+            }
+            const unsigned slot = seq % (unsigned)h->comm.ring;
+            comm_wait(h, seq, slot, n, h->stream);
+            const size_t img0 = (size_t)slot * nimg;
+            CK(cudaMemcpyAsync(cs.h_counts, h->pb.comm.counts[h->comm.rank] + img0, sizeof(int) * nimg, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(cs.h_dets, h->pb.comm.dets[h->comm.rank] + img0 * h->cfg.max_faces, sizeof(rf_det) * nimg * h->cfg.max_faces, cudaMemcpyDeviceToHost,
+                               h->stream));
+            CK(cudaMemcpyAsync(h->comm.h_err, h->comm.d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            CK(cudaMemcpyAsync(sl.h_counts, h->pb.out_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(sl.h_dets, h->pb.out_dets, sizeof(rf_det) * (size_t)n * h->cfg.max_faces, cudaMemcpyDeviceToHost, h->stream));
+        }
         CK(cudaEventRecord(sl.ev_done, h->stream));
         sl.n = n;
         sl.busy = true;
+        sl.gather = gather;
         *ticket = (int)h->submit_seq++;
     } catch (const CudaFail &f) { return fail_cuda(h, f); }
     return RF_OK;
 }
 
-int rf_collect_batch(rf_handle h, int ticket, rf_face *out_faces, int *out_counts, int32_t *out_idx) {
+int rf_submit_batch(rf_handle h, const uint8_t *const *imgs, int n, float thr, float nms, int *ticket) {
+    return submit_impl(h, imgs, n, thr, nms, ticket, false);
+}
+int rf_submit_batch_allgather(rf_handle h, const uint8_t *const *imgs, int n, float thr, float nms, int *ticket) {
+    return submit_impl(h, imgs, n, thr, nms, ticket, true);
+}
+
+static int collect_impl(rf_handle h, int ticket, rf_face *out_faces, int *out_counts, int32_t *out_idx, bool gather) {
     if (!h) return RF_ERR_INVALID_ARG;
     if ((unsigned)ticket != h->collect_seq) return fail(h, RF_ERR_INVALID_ARG, fmt("rf_collect_batch: ticket %d out of order (next is %u)", ticket, h->collect_seq));
     rf_handle_s::Slot &sl = h->slots[h->collect_seq % RF_PIPELINE_DEPTH];
     if (!sl.busy) return fail(h, RF_ERR_INVALID_ARG, "rf_collect_batch: nothing submitted under this ticket");
+    if (sl.gather != gather) return fail(h, RF_ERR_INVALID_ARG, "rf_collect_batch: ticket was submitted with the other (all-gather / local) entry point");
     try {
         CK(cudaSetDevice(h->device));
         CK(cudaEventSynchronize(sl.ev_done));
     } catch (const CudaFail &f) { return fail_cuda(h, f); }
     const int mf = h->cfg.max_faces;
-    for (int i = 0; i < sl.n; i++) {
-        const int k = sl.h_counts[i];
+    const rf_det *dets = sl.h_dets;
+    const int *counts = sl.h_counts;
+    int nimg = sl.n;
+    if (gather) {
+        Comm::Slot &cs = h->comm.slots[h->collect_seq % RF_PIPELINE_DEPTH];
+        dets = cs.h_dets; counts = cs.h_counts;
+        if (*h->comm.h_err) {
+            sl.busy = false;
+            h->collect_seq++;
+            return fail(h, RF_ERR_CUDA, fmt("multi-GPU exchange: rank %u never delivered its records of this step", *h->comm.h_err - 1));
+        }
+        // rank r's image i at r * max_batch + i; images beyond a rank's n are reported empty
+        for (int r = 0; r < h->comm.world; r++)
+            for (int i = sl.n; i < h->cfg.max_batch; i++)
+                if (out_counts) out_counts[r * h->cfg.max_batch + i] = 0;
+        for (int r = 0; r < h->comm.world; r++)
+            for (int i = 0; i < sl.n; i++) {
+                const size_t g = (size_t)r * h->cfg.max_batch + i;
+                const int k = std::min(counts[g], mf);
+                if (out_counts) out_counts[g] = k;
+                for (int j = 0; j < k; j++) {
+                    const rf_det &d = dets[g * mf + j];
+                    if (out_faces) out_faces[g * mf + j] = d.face;
+                    if (out_idx) out_idx[g * mf + j] = d.anchor_index;
+                }
+            }
+        sl.busy = false;
+        h->collect_seq++;
+        return RF_OK;
+    }
+    for (int i = 0; i < nimg; i++) {
+        const int k = counts[i];
         if (out_counts) out_counts[i] = k;
         for (int j = 0; j < k; j++) {
-            const rf_det &d = sl.h_dets[(size_t)i * mf + j];
+            const rf_det &d = dets[(size_t)i * mf + j];
             if (out_faces) out_faces[(size_t)i * mf + j] = d.face;
             if (out_idx) out_idx[(size_t)i * mf + j] = d.anchor_index;
         }
@@ -621,13 +702,26 @@ int rf_collect_batch(rf_handle h, int ticket, rf_face *out_faces, int *out_count
     return RF_OK;
 }
 
+int rf_collect_batch(rf_handle h, int ticket, rf_face *out_faces, int *out_counts, int32_t *out_idx) {
+    return collect_impl(h, ticket, out_faces, out_counts, out_idx, false);
+}
+int rf_collect_batch_allgather(rf_handle h, int ticket, rf_face *out_faces, int *out_counts, int32_t *out_idx) {
+    return collect_impl(h, ticket, out_faces, out_counts, out_idx, true);
+}
+int rf_detect_batch_allgather(rf_handle h, const uint8_t *const *imgs, int n, float thr, float nms, rf_face *out_faces, int *out_counts, int32_t *out_idx) {
+    int t = 0;
+    int rc = rf_submit_batch_allgather(h, imgs, n, thr, nms, &t);
+    if (rc) return rc;
+    return rf_collect_batch_allgather(h, t, out_faces, out_counts, out_idx);
+}
+
 static void ensure_merge_buffers(rf_handle h) {
     PostBuffers &pb = h->pb_merge;
     if (pb.cand_keys) return;
     const int A = h->cfg.max_batch * h->cfg.max_faces;       // every view may contribute max_faces candidates
     int ap2 = 1;
     while (ap2 < A) ap2 <<= 1;
-    pb.anchors_per_image = A; pb.anchors_pow2 = ap2; pb.max_faces = h->cfg.max_faces;
+    pb.anchors_per_image = A; pb.anchors_pow2 = ap2; pb.max_faces = h->cfg.max_faces; pb.max_batch = 1;
     CK(cudaMalloc(&pb.cand_keys, sizeof(unsigned long long) * (size_t)A));
     CK(cudaMalloc(&pb.cand_recs, sizeof(rf_det) * (size_t)A));
     CK(cudaMalloc(&pb.cand_count, sizeof(int)));

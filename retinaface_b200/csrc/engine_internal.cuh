@@ -69,8 +69,25 @@ struct Step {
 }  // namespace rf_eng
 using namespace rf_eng;
 
+namespace rf_eng {
+// multi-GPU exchange state of a handle (comm.cu)
+struct Comm {
+    int rank = 0, world = 1, ring = 0;
+    bool ready = false;
+    unsigned char *window = nullptr;       // this rank's gather window (device)
+    size_t bytes = 0;
+    unsigned char *peer[RF_COMM_MAX_WORLD] = {nullptr};
+    bool opened[RF_COMM_MAX_WORLD] = {false};
+    unsigned seq = 0;                      // steps exchanged so far
+    unsigned *d_err = nullptr, *h_err = nullptr;
+    unsigned char blob[128] = {0};
+    struct Slot { rf_det *h_dets = nullptr; int *h_counts = nullptr; } slots[RF_PIPELINE_DEPTH];   // pinned, [world][max_batch]...
+};
+}  // namespace rf_eng
+
 struct rf_handle_s {
     rf_config cfg{};
+    rf_eng::Comm comm;
     std::string caffemodel, table;
     std::string err;
     Model model;
@@ -129,7 +146,7 @@ struct rf_handle_s {
         int *h_counts = nullptr;
         cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
         int n = 0;
-        bool busy = false;
+        bool busy = false, gather = false;
     } slots[RF_PIPELINE_DEPTH];
     cudaStream_t copy_stream = nullptr;
     unsigned submit_seq = 0, collect_seq = 0;
@@ -253,6 +270,9 @@ std::vector<__half> pack_tc_weights(const std::vector<const FoldedConv *> &cs, s
 void build_plan_tiles(rf_handle h);         // RF_PREC_FP16 with tensor cores: tile chains (tile_chain.cuh) + round-1 kernels where no chain fits
 cudaError_t tile_init();
 std::string describe_chains(rf_handle h);
+// ---- exported by comm.cu --------------------------------------------------------------------------------------------
+void comm_release(rf_handle h);
+void comm_wait(rf_handle h, unsigned seq, unsigned slot, int n, cudaStream_t s);
 // ---- exported by plan_i8.cu -----------------------------------------------------------------------------------------
 void build_plan_i8(rf_handle h);
 cudaError_t tc_init_i8();

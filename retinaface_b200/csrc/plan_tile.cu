@@ -157,7 +157,7 @@ int add_head(TileChain &c, int in_buf, const FoldedConv *cs[3]) {
 
 // ---- finalisation: halos, rows, shared-memory placement, TMEM sets, kernel arguments --------------------------------------
 // returns false when the chain does not fit with TH rows per tile
-bool finalize_chain(rf_handle h, TileChain &c, int TH, int max_faces) {
+bool finalize_chain(rf_handle h, TileChain &c, int TH, int max_faces, bool resident) {
     const int ns = (int)c.stages.size(), nb = (int)c.bufs.size();
     if (ns > TCH_MAX_STAGES || nb > TCH_MAX_BUFS) return false;
     const int Wl = c.W + 2;
@@ -187,7 +187,7 @@ bool finalize_chain(rf_handle h, TileChain &c, int TH, int max_faces) {
     TchArgs &a = c.args;
     a = TchArgs{};
     a.nstages = ns; a.nbufs = nb;
-    a.Wl = Wl; a.slack = 8; a.HT = HT; a.TH = TH;      // slack: the tap at (-1, -1) of a buffer's first computed position reads one position before row 1
+    a.Wl = Wl; a.HT = HT; a.TH = TH;
     a.W = c.W; a.H = c.H;
     a.tiles_per_img = (c.H + TH - 1) / TH;
     a.in_s2 = c.in_s2; a.in_C = c.in_C;
@@ -200,6 +200,9 @@ bool finalize_chain(rf_handle h, TileChain &c, int TH, int max_faces) {
         tb.slabs = std::max(1, lb.C / 64);
         tb.rows_lo = HT - lb.halo;
         tb.nrows = TH + 2 * lb.halo;
+        // positions in front of the first row: the (-1, -1) tap of the first computed position reads one back; TMA-loaded
+        // buffers need their row 0 128-byte aligned (8), TMA-stored ones their position (row, lx = 1) (7 for rows < 128 bytes)
+        tb.slack = (lb.stored && tb.row < 128) ? 7 : 8;
         if (lb.is_merge) {
             a.merge_rows = (TH + 2 * HT) / 2 + 3;
             tb.rows_lo = 0; tb.nrows = a.merge_rows;
@@ -211,13 +214,13 @@ bool finalize_chain(rf_handle h, TileChain &c, int TH, int max_faces) {
             const int Hp = TH + 2 * c.stages[0].hs + 1;           // rows of each parity plane
             if (2 * Hp > 256) return false;
             tb.rows_lo = HT - c.stages[0].hs - 1; tb.nrows = Hp;
-            tb.slab_stride = round_up((a.slack + Hp * Wl + 8) * tb.row, 1024);
+            tb.slab_stride = round_up((tb.slack + Hp * Wl + 8) * tb.row, 1024);
             a.plane_stride = tb.slabs * tb.slab_stride;
             bytes[b] = 4 * a.plane_stride;
             a.in_bytes = 4u * (unsigned)tb.slabs * (unsigned)(std::min(lb.C, 64) * 2 * Wl * Hp);
             continue;
         }
-        tb.slab_stride = round_up((a.slack + tb.nrows * Wl + 8) * tb.row, 1024);
+        tb.slab_stride = round_up((tb.slack + tb.nrows * Wl + 8) * tb.row, 1024);
         bytes[b] = tb.slabs * tb.slab_stride;
         if (b == 0) a.in_bytes = (unsigned)tb.slabs * (unsigned)(std::min(lb.C, 64) * 2 * Wl * tb.nrows);
     }
@@ -266,7 +269,7 @@ bool finalize_chain(rf_handle h, TileChain &c, int TH, int max_faces) {
         const TchBuf &bi = a.buf[ls.in_buf];
         const int ntile = (st.nrows * Wl + 127) / 128;
         mt += ntile * (ls.type == TCH_DWPW ? 2 : 1);
-        const int pos0 = (ls.type == TCH_DWPW && ls.stride == 2) ? a.slack : a.slack + (st.rows_lo - bi.rows_lo) * Wl;
+        const int pos0 = (ls.type == TCH_DWPW && ls.stride == 2) ? bi.slack : bi.slack + (st.rows_lo - bi.rows_lo) * Wl;
         const int last_plane = (ls.type == TCH_DWPW && ls.stride == 2) ? 3 * a.plane_stride : 0;
         read_end = std::max(read_end, bi.off + last_plane + (bi.slabs - 1) * bi.slab_stride + (pos0 + ntile * 128 + Wl + 2) * bi.row);
     }
@@ -281,8 +284,8 @@ bool finalize_chain(rf_handle h, TileChain &c, int TH, int max_faces) {
         if (last_writer < 0 || a.st[last_writer].store_buf >= 0) return false;
         a.st[last_writer].store_buf = b; a.st[last_writer].store_map = c.nstores;
         c.store_buf_of[c.nstores] = b; c.store_C[c.nstores] = c.bufs[b].C;
-        // TMA store source must be 128-byte aligned
-        if (((a.slack + (HT - a.buf[b].rows_lo) * Wl) * a.buf[b].row) % 128) return false;
+        // TMA store sources (position (row, lx = 1) of every owned row) must be 128-byte aligned
+        if (((a.buf[b].slack + 1) * a.buf[b].row) % 128 || (Wl * a.buf[b].row) % 128) return false;
         c.nstores++;
     }
     if (c.merge_tensor >= 0) {
@@ -297,12 +300,25 @@ bool finalize_chain(rf_handle h, TileChain &c, int TH, int max_faces) {
     if (set_cols > 512) return false;
     // weights, bias arena, NMS scratch behind the buffers
     const int nms_need = c.fused_nms ? (int)((sizeof(NmsSmem) + 15) / 16 * 16 + sizeof(int) * (size_t)max_faces) : 0;
-    a.wd_smem = round_up(top, 1024);
-    a.wp_smem = a.wd_smem + round_up(wd_max, 128);
-    const int wp_region = std::max(round_up(wp_max, 128), round_up(nms_need, 128));
-    a.bias_smem = a.wp_smem + wp_region;
+    a.resident = resident ? 1 : 0;
+    int cursor = round_up(top, 1024);
+    if (resident) {
+        // every stage keeps its own weight regions for the CTA's lifetime
+        for (int s = 0; s < ns; s++) {
+            a.st[s].wd_smem = cursor; cursor += round_up(a.st[s].wd_bytes, 128);
+            a.st[s].wp_smem = cursor; cursor += round_up(a.st[s].wp_bytes, 128);
+        }
+        a.wd_smem = a.wp_smem = cursor;
+        // NMS scratch: the input tile's region (dead by then, never TMA-stored) when large enough
+        if (nms_need && bytes[0] >= nms_need) a.head.nms_smem = a.buf[0].off;
+        else { a.head.nms_smem = cursor; cursor += round_up(nms_need, 128); }
+    } else {
+        a.wd_smem = cursor; cursor += round_up(wd_max, 128);
+        a.wp_smem = cursor; cursor += std::max(round_up(wp_max, 128), round_up(nms_need, 128));
+        a.head.nms_smem = a.wp_smem;
+    }
+    a.bias_smem = cursor;
     a.bias_floats = (int)bias.size();
-    a.head.nms_smem = a.wp_smem;
     a.smem_bytes = std::max(a.bias_smem + a.bias_floats * 4, read_end) + 1024;      // + alignment slack of the dynamic base
     if (a.smem_bytes > TCH_SMEM_LIMIT) return false;
     c.TH = TH;
@@ -325,26 +341,33 @@ void commit_chain(Builder &B, TileChain &c) {
     c.bias_off = B.add_weights(h->tile_bias_tmp);
 }
 
-// picks the tile height: among the heights that fit, the one with the least (waves x MMA tiles per CTA), ties to the taller
-bool choose_tile(rf_handle h, TileChain &c, int max_batch, int max_faces, int force_th) {
-    double best = 1e30;
-    int best_th = 0;
-    for (int th = 1; th <= std::min(c.H, 32); th++) {
-        if (force_th > 0 && th != force_th) continue;
-        if (!finalize_chain(h, c, th, max_faces)) continue;
-        const long tiles = (long)max_batch * c.args.tiles_per_img;
-        const double waves = std::ceil((double)tiles / 148.0);
-        const double cost = waves * (c.mtiles + 2.0 * c.stages.size() + 4.0);      // + per-stage / per-tile hand-off latencies
-        if (cost <= best) { best = cost; best_th = th; }
-    }
-    if (!best_th) return false;
-    return finalize_chain(h, c, best_th, max_faces);
-}
-
 int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
 }
+
+// picks the tile height: among the heights that fit, the one with the least (waves x MMA tiles per CTA), ties to the taller
+bool choose_tile(rf_handle h, TileChain &c, int max_batch, int max_faces, int force_th) {
+    double best = 1e30;
+    int best_th = 0;
+    bool best_res = false;
+    const bool allow_res = env_int("RF_TILE_RESIDENT", 1) != 0;
+    for (int th = 1; th <= std::min(c.H, 32); th++) {
+        if (force_th > 0 && th != force_th) continue;
+        for (int res = allow_res ? 1 : 0; res >= 0; res--) {
+            if (!finalize_chain(h, c, th, max_faces, res != 0)) continue;
+            const long tiles = (long)max_batch * c.args.tiles_per_img;
+            const double waves = std::ceil((double)tiles / 148.0);
+            // MMA tiles + per-stage hand-offs (streamed weights: one exposed load per stage) + per-tile set-up
+            const double cost = waves * (c.mtiles + (res ? 1.0 : 4.0) * c.stages.size() + 4.0);
+            if (cost < best || (cost == best && th > best_th)) { best = cost; best_th = th; best_res = res != 0; }
+            break;      // resident fits: no need to look at streaming for this height
+        }
+    }
+    if (!best_th) return false;
+    return finalize_chain(h, c, best_th, max_faces, best_res);
+}
+
 int forced_th(const std::string &chain) {
     // RF_TILE_TH="A=4,B=2,ssh2=7": per-chain tile heights for experiments
     const char *v = getenv("RF_TILE_TH");
@@ -377,7 +400,7 @@ void launch_chain(rf_handle h, const std::shared_ptr<TileChain> &cp, int n, cuda
     if (c.in_s2) maps.in = make_map(h->tptr(c.in_tensor), c.in_C, c.in_W, c.in_H, n, bc, 2 * a.Wl, 2 * b0.nrows, 2);
     else maps.in = make_map(h->tptr(c.in_tensor), c.in_C, c.in_W, c.in_H, n, bc, a.Wl, b0.nrows, 1);
     if (c.merge_tensor >= 0) maps.aux = make_map(h->tptr(c.merge_tensor), 64, c.W / 2, c.H / 2, n, 64, c.W / 2 + 2, a.merge_rows, 1);
-    for (int i = 0; i < c.nstores; i++) maps.st[i] = make_map(h->tptr(c.bufs[c.store_buf_of[i]].store_tensor), c.store_C[i], c.W, c.H, n, std::min(c.store_C[i], 64), a.Wl, a.TH, 1);
+    for (int i = 0; i < c.nstores; i++) maps.st[i] = make_map(h->tptr(c.bufs[c.store_buf_of[i]].store_tensor), c.store_C[i], c.W, c.H, n, std::min(c.store_C[i], 64), c.W, 1, 1);
     if (c.level >= 0) {
         a.head.lv = h->lv[c.level];
         a.head.pb = h->pb;
@@ -418,8 +441,9 @@ std::string describe_chains(rf_handle h) {
     for (auto &cp : h->chains) {
         const TileChain &c = *cp;
         const TchArgs &a = c.args;
-        out += fmt("%s: %dx%d map, TH=%d HT=%d Wl=%d, %d tiles/image, %d stages, %d MMA tiles/tile, smem %d B, TMEM %d x %d cols, stores %d\n", c.name.c_str(), c.W, c.H,
-                   a.TH, a.HT, a.Wl, a.tiles_per_img, a.nstages, c.mtiles, a.smem_bytes, a.nsets, a.set_cols, c.nstores);
+        out += fmt("%s: %dx%d map, TH=%d HT=%d Wl=%d, %d tiles/image, %d stages, %d MMA tiles/tile, smem %d B (%s weights), TMEM %d x %d cols, stores %d\n",
+                   c.name.c_str(), c.W, c.H, a.TH, a.HT, a.Wl, a.tiles_per_img, a.nstages, c.mtiles, a.smem_bytes, a.resident ? "resident" : "streamed", a.nsets,
+                   a.set_cols, c.nstores);
     }
     return out;
 }
@@ -439,11 +463,11 @@ cudaError_t tile_init() {
 // RF_TILE_MASK bits: which parts of the FP16 plan run as tile chains (default all); the others use the round-1 kernels
 enum { TM_A = 1, TM_B = 2, TM_CD = 4, TM_E = 8, TM_AGGR = 16, TM_SSH = 32, TM_HEAD = 64, TM_NMS = 128 };
 
-void build_plan_tiles(rf_handle h) {
+// builds the plan for one mask; false: the predictors could not be fused at all three levels (the caller retries without)
+static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
     Builder B{h, h->cfg.net_h, h->cfg.net_w};
     const Model &m = h->model;
     const int H = h->cfg.net_h, W = h->cfg.net_w, mb = h->cfg.max_batch, mf = h->cfg.max_faces;
-    unsigned mask = (unsigned)env_int("RF_TILE_MASK", 0xff);
     if (!(mask & TM_SSH)) mask &= ~(TM_HEAD | TM_NMS);
     if (!(mask & TM_HEAD)) mask &= ~TM_NMS;
     const double es = 2;
@@ -619,7 +643,7 @@ void build_plan_tiles(rf_handle h) {
     if (!all_heads) {
         // some level's predictors are not fused: none may be (one decode kernel covers all levels)
         for (auto &c : ssh_chain)
-            if (c && c->level >= 0) throw PlanFail{RF_ERR_UNSUPPORTED, "SSH tile chains with fused predictors need all three levels to fit; set RF_TILE_MASK without 64"};
+            if (c && c->level >= 0) return false;
         plan_heads_and_nms<__half>(B, true, true);
     } else {
         h->head_step = (int)h->steps.size() - 1;          // the stride-8 SSH chain (last step) emits the last candidates
@@ -627,6 +651,20 @@ void build_plan_tiles(rf_handle h) {
         if (!(mask & TM_NMS)) plan_heads_and_nms<__half>(B, false, true);
     }
     h->tile_mask = mask;
+    return true;
+}
+
+void build_plan_tiles(rf_handle h) {
+    const unsigned mask = (unsigned)env_int("RF_TILE_MASK", 0xff);
+    for (unsigned m : {mask, mask & ~(unsigned)(TM_HEAD | TM_NMS)}) {
+        // a failed attempt leaves no trace
+        h->steps.clear(); h->tensors.clear(); h->tensor_by_name.clear(); h->chains.clear();
+        h->wstage.clear(); h->wstage_h.clear(); h->wstage_q.clear();
+        h->head_step = h->nms_step = -1; h->tile_expected = 0;
+        for (int &f : h->feat_tensor) f = -1;
+        if (build_tiles_with_mask(h, m)) return;
+    }
+    throw PlanFail{RF_ERR_UNSUPPORTED, "no tile-chain plan fits this network size; create the handle with RF_FLAG_LEGACY_TC"};
 }
 
 }  // namespace rf_eng

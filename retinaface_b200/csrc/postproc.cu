@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms(const PostParams *__restric
     __shared__ NmsSmem S;
     pdl_trigger();
     pdl_wait();
-    nms_image<NMS_THREADS, false>(blockIdx.x, threadIdx.x, params->nms_thr, pb, S, s_kept, [] { __syncthreads(); });
+    nms_image<NMS_THREADS, false>(blockIdx.x, threadIdx.x, params->nms_thr, params, pb, S, s_kept, [] { __syncthreads(); });
 }
 
 

@@ -4,6 +4,17 @@
 
 namespace rf {
 
+// Multi-GPU exchange of the final detections, fused into the NMS: the CTA that finishes an image stores its
+// kept records straight into the gather window of EVERY rank (peer device memory over NVLink, mapped through CUDA IPC),
+// then raises that image's flag there.  Window of one rank: [ring][world][max_batch] x {count, flag, max_faces records}.
+constexpr int RF_COMM_MAX_WORLD = RF_COMM_MAX_WORLD_SIZE;
+struct CommView {
+    int world, rank, ring;
+    rf_det *dets[RF_COMM_MAX_WORLD];       // rank p's window: [ring][world][max_batch][max_faces]
+    int *counts[RF_COMM_MAX_WORLD];        //                  [ring][world][max_batch]
+    unsigned *flags[RF_COMM_MAX_WORLD];    //                  [ring][world][max_batch]  == seq once the image's records have landed
+};
+
 struct PostBuffers {
     // per image i (capacity = anchors_per_image A):
     unsigned long long *cand_keys;  // [B][A]   sort keys of candidates in append order
@@ -18,6 +29,8 @@ struct PostBuffers {
     int anchors_per_image;
     int anchors_pow2;
     int max_faces;
+    int max_batch;
+    CommView comm;                  // world <= 1: single GPU, no exchange
 };
 
 struct HeadWeights {

@@ -97,7 +97,7 @@ struct NmsSmem {
 // memory; beyond that (stress inputs) keys / flags use the global scratch of PostBuffers.
 // `acquire`: the candidates were written by OTHER CTAs (last-block pattern): read them through L2 (__ldcg).
 template <int NT, bool ACQUIRE, typename Sync>
-__device__ __forceinline__ void nms_image(int img, int tid, float thr, const PostBuffers &pb, NmsSmem &S, int *s_kept, Sync sync) {
+__device__ __forceinline__ void nms_image(int img, int tid, float thr, const PostParams *params, const PostBuffers &pb, NmsSmem &S, int *s_kept, Sync sync) {
     const int A = pb.anchors_per_image;
     int n = ACQUIRE ? __ldcg(&pb.cand_count[img]) : pb.cand_count[img];
     if (n > A) n = A;
@@ -175,15 +175,26 @@ __device__ __forceinline__ void nms_image(int img, int tid, float thr, const Pos
     // gather: 16 floats per record, one thread per float
     const float *src = reinterpret_cast<const float *>(recs);
     float *dst = reinterpret_cast<float *>(pb.out_dets + (size_t)img * pb.max_faces);
+    const unsigned seq = pb.comm.world > 1 ? params->comm_seq : 0u;
+    const size_t wslot = seq ? ((size_t)params->comm_slot * pb.comm.world + pb.comm.rank) * pb.max_batch + img : 0;
     for (int t = tid; t < kept * 16; t += NT) {
         int k = t >> 4, w = t & 15;
         unsigned e = (unsigned)(keys[s_kept[k]] & 0xffffffffu);
-        dst[t] = ACQUIRE ? __ldcg(&src[(size_t)e * 16 + w]) : src[(size_t)e * 16 + w];
+        const float v = ACQUIRE ? __ldcg(&src[(size_t)e * 16 + w]) : src[(size_t)e * 16 + w];
+        dst[t] = v;
+        if (seq)     // the same record into every rank's window (peer memory; this rank's own window included)
+            for (int p = 0; p < pb.comm.world; p++) reinterpret_cast<float *>(pb.comm.dets[p] + wslot * pb.max_faces)[t] = v;
     }
     if (tid == 0) {
         pb.out_counts[img] = kept;
         pb.out_total_kept[img] = total;
         pb.cand_count[img] = 0;  // self-cleaning for the next launch
+        if (seq) for (int p = 0; p < pb.comm.world; p++) pb.comm.counts[p][wslot] = kept;
+    }
+    if (seq) {
+        __threadfence_system();  // records + count are visible system-wide before the flag
+        sync();
+        if (tid < pb.comm.world) *reinterpret_cast<volatile unsigned *>(&pb.comm.flags[tid][wslot]) = seq;
     }
     sync();                      // S may be reused by the caller
 }

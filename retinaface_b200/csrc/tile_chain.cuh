@@ -55,6 +55,7 @@ struct TchBuf {
     int slab_stride;    // bytes between slabs
     int rows_lo;        // local row held at position index `slack`
     int nrows;          // rows held
+    int slack;          // positions in front of row rows_lo (>= 1: the (-1, -1) tap of the first computed position reads one back)
 };
 
 struct TchStage {
@@ -65,6 +66,7 @@ struct TchStage {
     int rows_lo, nrows;       // local rows this stage computes
     int wd_off, wd_bytes;     // depthwise diagonal B tiles in the weight arena
     int wp_off, wp_bytes;     // B image [K/8][N][8] (HEAD: hi image then lo image)
+    int wd_smem, wp_smem;     // resident weights: this stage's own regions in shared memory
     int bias_dw, bias_pw;     // float offsets into the bias arena
     int store_buf, store_map; // -1 | buffer whose owned rows [HT, HT + TH) are TMA-stored once the stage is complete
     unsigned char ob_buf[16], ob_c16[16], ob_relu[16];   // per 16-column output block: buffer, channel offset / 16, ReLU
@@ -85,10 +87,12 @@ struct TchArgs {
     int nstages, nbufs;
     TchStage st[TCH_MAX_STAGES];
     TchBuf buf[TCH_MAX_BUFS];
-    int Wl, slack, HT, TH;
+    int Wl, HT, TH;
     int W, H, nimg, tiles_per_img, ntiles;
     int nsets, set_cols;
     int wd_smem, wp_smem, bias_smem, smem_bytes;     // byte offsets in dynamic shared memory / total
+    int resident;             // 1: the weights of ALL stages stay in shared memory for the CTA's lifetime (loaded once, before
+                              // griddepcontrol.wait); 0: streamed per stage through the wd / wp buffers
     unsigned *dbg;            // host-mapped word: code of the hand-off a timed-out wait was stuck on (0: none)
     const unsigned char *warena;
     const float *bias;
@@ -132,10 +136,16 @@ __device__ __forceinline__ void wait(uint64_t *bar, unsigned parity, unsigned *d
             : "r"(tc::smem_u32(bar)), "r"(parity)
             : "memory");
         if (!done && ++spins > (1u << 22)) {
-            if (dbg) { dbg[0] = code | (blockIdx.x << 20); __threadfence_system(); }
+            if (dbg) { *reinterpret_cast<volatile unsigned *>(dbg) = code | (blockIdx.x << 20); __threadfence_system(); __nanosleep(2000000); }
             __trap();
         }
     }
+}
+// the same for a whole warp: lanes may leave the polling loop in different iterations; the warp-collective (.sync.aligned)
+// tcgen05 instructions that follow need it converged again
+__device__ __forceinline__ void wait_warp(uint64_t *bar, unsigned parity, unsigned *dbg, unsigned code) {
+    wait(bar, parity, dbg, code);
+    __syncwarp();
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -159,6 +169,35 @@ __device__ __forceinline__ uint64_t sw_desc(uint32_t addr, uint32_t row) {
     d |= (uint64_t)1 << 46;
     d |= layout << 61;
     return d;
+}
+// Descriptor words.  A shared-memory matrix descriptor is {lo: (addr >> 4) [0,14) | LBO >> 4 [16,30)} {hi: SBO >> 4 [0,14) |
+// version 1 [14] | layout [29,32)}: moving the operand by a multiple of 16 bytes is ONE 32-bit add on the low word (shared
+// memory is < 256 KB, the address field cannot carry out), so the issue loops below precompute every tap / K-step offset.
+__device__ __forceinline__ uint32_t a_desc_hi(uint32_t row) {
+    const uint32_t layout = row == 128 ? 2u : (row == 64 ? 4u : 6u);
+    return ((8u * row) >> 4) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint32_t a_desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t b_desc_hi() { return (128u >> 4) | (1u << 14); }                       // K-major, no swizzle, SBO 128
+__device__ __forceinline__ uint32_t b_desc_lo(uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16); }
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // D[tmem] (+)= A[tmem, packed FP16] * B[smem desc]
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -233,12 +272,30 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
         // =========================================== TMA producer ===========================================
         if (lane == 0) {
             const unsigned bias_bytes = (unsigned)a.bias_floats * 4u;
-            tc::mbar_expect_tx(&bar_bias, bias_bytes);
+            unsigned const_bytes = bias_bytes;
+            if (a.resident) for (int s = 0; s < a.nstages; s++) const_bytes += (unsigned)(a.st[s].wd_bytes + a.st[s].wp_bytes);
+            tc::mbar_expect_tx(&bar_bias, const_bytes);
             tch::bulk_g2s_u32(sbase + a.bias_smem, a.bias, bias_bytes, &bar_bias);       // constants: independent of earlier kernels
+            if (a.resident)
+                for (int s = 0; s < a.nstages; s++) {
+                    if (a.st[s].wd_bytes) tch::bulk_g2s_u32(sbase + a.st[s].wd_smem, a.warena + a.st[s].wd_off, (unsigned)a.st[s].wd_bytes, &bar_bias);
+                    tch::bulk_g2s_u32(sbase + a.st[s].wp_smem, a.warena + a.st[s].wp_off, (unsigned)a.st[s].wp_bytes, &bar_bias);
+                }
             tch::prefetch_map(&maps.in);
             pdl_wait();                                                                   // activations of earlier kernels from here on
             unsigned wdc = 0, wpc = 0, sc = 0;
             const TchBuf &B0 = a.buf[0];
+            // owned rows of a finished buffer -> global, one box {<= 64 channels, W, 1} per row and slab starting at image column 0
+            // (TMA stores reject negative coordinates -- tools/umma_probe.cu "store" -- so the zero column at lx = 0 stays behind)
+            auto store_rows = [&](const TchBuf &BS, int map, int ty, int b) {
+                for (int rr = 0; rr < a.TH; rr++) {
+                    const int y = ty * a.TH + rr;
+                    if (y >= a.H) break;
+                    for (int k = 0; k < BS.slabs; k++)
+                        tch::tma_store_4d(&maps.st[map], sbase + BS.off + k * BS.slab_stride + (BS.slack + (a.HT - BS.rows_lo + rr) * Wl + 1) * BS.row, k * 64, 0, y, b);
+                }
+                tch::bulk_commit();
+            };
             for (int tile = blockIdx.x, it = 0; tile < a.ntiles; tile += gridDim.x, it++) {
                 const int b = tile / a.tiles_per_img, ty = tile - b * a.tiles_per_img;
                 const int Y0 = ty * a.TH - a.HT;                 // image row of local row 0; image column of local column 0 is -1
@@ -247,12 +304,12 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                 const int in_slabs = (a.in_C + 63) >> 6;
                 if (!a.in_s2) {
                     for (int s = 0; s < in_slabs; s++)
-                        tch::tma_load_4d(sbase + B0.off + s * B0.slab_stride + a.slack * B0.row, &maps.in, &bar_in, s * 64, -1, Y0 + B0.rows_lo, b);
+                        tch::tma_load_4d(sbase + B0.off + s * B0.slab_stride + B0.slack * B0.row, &maps.in, &bar_in, s * 64, -1, Y0 + B0.rows_lo, b);
                 } else {
                     // plane (py, px) element (pr, lx) = input(2 * (Y0 + rows_lo0 - 1 + pr) + py, 2 * (lx - 1) + px)
                     for (int k = 0; k < 4; k++)
                         for (int s = 0; s < in_slabs; s++)
-                            tch::tma_load_4d(sbase + B0.off + k * a.plane_stride + s * B0.slab_stride + a.slack * B0.row, &maps.in, &bar_in, s * 64,
+                            tch::tma_load_4d(sbase + B0.off + k * a.plane_stride + s * B0.slab_stride + B0.slack * B0.row, &maps.in, &bar_in, s * 64,
                                              -2 + (k & 1), 2 * (Y0 + a.st[0].rows_lo - 1) + (k >> 1), b);
                 }
                 if (a.merge_C) {
@@ -263,39 +320,29 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                 }
                 for (int s = 0; s < a.nstages; s++, sc++) {
                     const TchStage &st = a.st[s];
-                    if (st.wd_bytes) {
-                        tch::wait(&bar_wd_empty, (wdc & 1) ^ 1, a.dbg, __LINE__);
-                        tc::mbar_expect_tx(&bar_wd_full, (unsigned)st.wd_bytes);
-                        tch::bulk_g2s_u32(sbase + a.wd_smem, a.warena + st.wd_off, (unsigned)st.wd_bytes, &bar_wd_full);
-                        wdc++;
+                    if (!a.resident) {
+                        if (st.wd_bytes) {
+                            tch::wait(&bar_wd_empty, (wdc & 1) ^ 1, a.dbg, __LINE__);
+                            tc::mbar_expect_tx(&bar_wd_full, (unsigned)st.wd_bytes);
+                            tch::bulk_g2s_u32(sbase + a.wd_smem, a.warena + st.wd_off, (unsigned)st.wd_bytes, &bar_wd_full);
+                            wdc++;
+                        }
+                        tch::wait(&bar_wp_empty, (wpc & 1) ^ 1, a.dbg, __LINE__);
+                        tc::mbar_expect_tx(&bar_wp_full, (unsigned)st.wp_bytes);
+                        tch::bulk_g2s_u32(sbase + a.wp_smem, a.warena + st.wp_off, (unsigned)st.wp_bytes, &bar_wp_full);
+                        wpc++;
                     }
-                    tch::wait(&bar_wp_empty, (wpc & 1) ^ 1, a.dbg, __LINE__);
-                    tc::mbar_expect_tx(&bar_wp_full, (unsigned)st.wp_bytes);
-                    tch::bulk_g2s_u32(sbase + a.wp_smem, a.warena + st.wp_off, (unsigned)st.wp_bytes, &bar_wp_full);
-                    wpc++;
                     // every phase of bar_stage is observed in order; stage s-1 is complete -> its TMA store
                     if (s > 0) {
                         tch::wait(&bar_stage, (sc - 1) & 1, a.dbg, __LINE__);
                         const TchStage &sp = a.st[s - 1];
-                        if (sp.store_buf >= 0) {
-                            const TchBuf &BS = a.buf[sp.store_buf];
-                            for (int k = 0; k < BS.slabs; k++)
-                                tch::tma_store_4d(&maps.st[sp.store_map], sbase + BS.off + k * BS.slab_stride + (a.slack + (a.HT - BS.rows_lo) * Wl) * BS.row,
-                                                  k * 64, -1, ty * a.TH, b);
-                            tch::bulk_commit();
-                        }
+                        if (sp.store_buf >= 0) store_rows(a.buf[sp.store_buf], sp.store_map, ty, b);
                     }
                 }
                 tch::wait(&bar_stage, (sc - 1) & 1, a.dbg, __LINE__);
                 {
                     const TchStage &sp = a.st[a.nstages - 1];
-                    if (sp.store_buf >= 0) {
-                        const TchBuf &BS = a.buf[sp.store_buf];
-                        for (int k = 0; k < BS.slabs; k++)
-                            tch::tma_store_4d(&maps.st[sp.store_map], sbase + BS.off + k * BS.slab_stride + (a.slack + (a.HT - BS.rows_lo) * Wl) * BS.row,
-                                              k * 64, -1, ty * a.TH, b);
-                        tch::bulk_commit();
-                    }
+                    if (sp.store_buf >= 0) store_rows(a.buf[sp.store_buf], sp.store_map, ty, b);
                 }
             }
             tch::bulk_wait0();       // global writes of the last stores are complete before the CTA exits
@@ -304,63 +351,72 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
         // =========================================== MMA issuer =============================================
         unsigned wdc = 0, wpc = 0, sc = 0, g = 0;
         unsigned use[2] = {0, 0}, dwuse[2] = {0, 0};
-        const uint32_t wd_addr = sbase + a.wd_smem, wp_addr = sbase + a.wp_smem;
+        if (a.resident) tch::wait_warp(&bar_bias, 0, a.dbg, __LINE__);       // every stage's weights are in shared memory
         for (int tile = blockIdx.x, it = 0; tile < a.ntiles; tile += gridDim.x, it++) {
-            tch::wait(&bar_in, it & 1, a.dbg, __LINE__);
-            if (a.merge_C) tch::wait(&bar_merge, it & 1, a.dbg, __LINE__);
+            tch::wait_warp(&bar_in, it & 1, a.dbg, __LINE__);
+            if (a.merge_C) tch::wait_warp(&bar_merge, it & 1, a.dbg, __LINE__);
             for (int s = 0; s < a.nstages; s++, sc++) {
                 const TchStage &st = a.st[s];
                 const TchBuf &BI = a.buf[st.in_buf];
-                if (sc > 0) tch::wait(&bar_stage, (sc - 1) & 1, a.dbg, __LINE__);      // inputs of this stage are in shared memory
-                if (st.wd_bytes) { tch::wait(&bar_wd_full, wdc & 1, a.dbg, __LINE__); wdc++; }
-                tch::wait(&bar_wp_full, wpc & 1, a.dbg, __LINE__); wpc++;
+                if (sc > 0) tch::wait_warp(&bar_stage, (sc - 1) & 1, a.dbg, __LINE__);      // inputs of this stage are in shared memory
+                if (!a.resident) {
+                    if (st.wd_bytes) { tch::wait_warp(&bar_wd_full, wdc & 1, a.dbg, __LINE__); wdc++; }
+                    tch::wait_warp(&bar_wp_full, wpc & 1, a.dbg, __LINE__); wpc++;
+                }
                 tc::tc_fence_after();
                 const int npos = st.nrows * Wl, ntile = (npos + 127) >> 7;
                 const int kpr = BI.row >> 5;                             // 16-channel K steps per row
                 // position index (in the input buffer) of this stage's position 0
-                const int pos0 = st.type == TCH_DWPW && st.stride == 2 ? a.slack : a.slack + (st.rows_lo - BI.rows_lo) * Wl;
-                const uint32_t in_addr = sbase + BI.off;
-                const uint32_t lbo_b = (uint32_t)st.N * 16;
+                const int pos0 = st.type == TCH_DWPW && st.stride == 2 ? BI.slack : BI.slack + (st.rows_lo - BI.rows_lo) * Wl;
+                const uint32_t rowq = (uint32_t)BI.row >> 4;              // 16-byte units per position
+                const uint32_t ahi = tch::a_desc_hi(BI.row), bhi = tch::b_desc_hi();
+                const uint32_t alo0 = tch::a_desc_lo(sbase + BI.off) + (uint32_t)pos0 * rowq;
+                const uint32_t tile_step = 128u * rowq;                   // one MMA tile further
+                const uint32_t slabq = (uint32_t)BI.slab_stride >> 4;
+                const uint32_t wp_addr = sbase + (a.resident ? st.wp_smem : a.wp_smem), wd_addr = sbase + (a.resident ? st.wd_smem : a.wd_smem);
                 if (st.type == TCH_DWPW) {
                     const int nk = st.Cin >> 4;
                     const uint32_t idesc16 = tch::idesc_f16(16), idescN = tch::idesc_f16(st.N);
+                    // per tap: operand shift (+ parity plane for stride 2), in 16-byte units
+                    uint32_t tapq[9];
+#pragma unroll
+                    for (int t = 0; t < 9; t++) {
+                        const int dy = t / 3 - 1, dx = t % 3 - 1;
+                        int shift, plane = 0;
+                        if (st.stride == 2) { plane = ((dy & 1) << 1) | (dx & 1); shift = (dy >= 0 ? Wl : 0) + (dx < 0 ? -1 : 0); }
+                        else shift = dy * Wl + dx;
+                        tapq[t] = (uint32_t)(shift * (int)rowq + plane * (a.plane_stride >> 4));
+                    }
+                    const uint32_t wdlo0 = tch::b_desc_lo(wd_addr, 256), wplo0 = tch::b_desc_lo(wp_addr, (uint32_t)st.N * 16);
                     auto issue_dw = [&](int m) {
                         const int set = a.nsets == 2 ? ((g + m) & 1) : 0;
-                        tch::wait(&bar_acc_empty[set], (use[set] & 1) ^ 1, a.dbg, __LINE__);
+                        tch::wait_warp(&bar_acc_empty[set], (use[set] & 1) ^ 1, a.dbg, __LINE__);
                         use[set]++;
                         tc::tc_fence_after();
                         if (lane == 0) {
                             const uint32_t d0 = tmem + set * a.set_cols;
+                            const uint32_t am = alo0 + (uint32_t)m * tile_step;
                             for (int k = 0; k < nk; k++) {
-                                const uint32_t abase = in_addr + (k / kpr) * BI.slab_stride + (k % kpr) * 32;
-                                for (int t = 0; t < 9; t++) {
-                                    const int dy = t / 3 - 1, dx = t % 3 - 1;
-                                    int shift, plane = 0;
-                                    if (st.stride == 2) { plane = ((dy & 1) << 1) | (dx & 1); shift = (dy >= 0 ? Wl : 0) + (dx < 0 ? -1 : 0); }
-                                    else shift = dy * Wl + dx;
-                                    const uint64_t ad = tch::sw_desc(abase + plane * a.plane_stride + (uint32_t)(pos0 + m * 128 + shift) * BI.row, BI.row);
-                                    const uint64_t bd = tc::smem_desc(wd_addr + (uint32_t)(t * nk + k) * 512, 256, 128);
-                                    tc::mma_f16(d0 + k * 16, ad, bd, idesc16, t > 0);
-                                }
+                                const uint32_t ak = am + (uint32_t)(k / kpr) * slabq + (uint32_t)(k % kpr) * 2u;
+                                const uint32_t bk = wdlo0 + (uint32_t)k * 32u;
+#pragma unroll
+                                for (int t = 0; t < 9; t++) tch::mma_ss(d0 + k * 16, ak + tapq[t], ahi, bk + (uint32_t)(t * nk) * 32u, bhi, idesc16, t > 0);
                             }
                             tc::mma_commit(&bar_dw_full[set]);
-                            if (m == ntile - 1) tc::mma_commit(&bar_wd_empty);
+                            if (m == ntile - 1 && !a.resident) tc::mma_commit(&bar_wd_empty);
                         }
                         __syncwarp();
                     };
                     auto issue_pw = [&](int m) {
                         const int set = a.nsets == 2 ? ((g + m) & 1) : 0;
-                        tch::wait(&bar_a16_full[set], dwuse[set] & 1, a.dbg, __LINE__);
+                        tch::wait_warp(&bar_a16_full[set], dwuse[set] & 1, a.dbg, __LINE__);
                         dwuse[set]++;
                         tc::tc_fence_after();
                         if (lane == 0) {
                             const uint32_t d0 = tmem + set * a.set_cols;
-                            for (int k = 0; k < nk; k++) {
-                                const uint64_t bd = tc::smem_desc(wp_addr + (uint32_t)(2 * k) * lbo_b, lbo_b, 128);
-                                tch::mma_f16_ts(d0 + st.Cin, d0 + k * 8, bd, idescN, k > 0);
-                            }
+                            for (int k = 0; k < nk; k++) tch::mma_ts(d0 + st.Cin, d0 + k * 8, wplo0 + (uint32_t)(2 * k * st.N), bhi, idescN, k > 0);
                             tc::mma_commit(&bar_acc_full[set]);
-                            if (m == ntile - 1) tc::mma_commit(&bar_wp_empty);
+                            if (m == ntile - 1 && !a.resident) tc::mma_commit(&bar_wp_empty);
                         }
                         __syncwarp();
                     };
@@ -376,28 +432,39 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                     const int nk = st.Cin >> 4;
                     const uint32_t idescN = tch::idesc_f16(st.N);
                     const int pieces = st.type == TCH_HEAD ? 2 : 1;
-                    const uint32_t piece_bytes = (uint32_t)st.taps * st.Cin * st.N * 2;
+                    const uint32_t pieceq = ((uint32_t)st.taps * st.Cin * st.N * 2) >> 4;
+                    const uint32_t wplo0 = tch::b_desc_lo(wp_addr, (uint32_t)st.N * 16);
+                    const uint32_t tapb = (uint32_t)(st.Cin >> 3) * st.N;      // B image: 16-byte units per tap
                     for (int m = 0; m < ntile; m++) {
                         const int set = a.nsets == 2 ? ((g + m) & 1) : 0;
-                        tch::wait(&bar_acc_empty[set], (use[set] & 1) ^ 1, a.dbg, __LINE__);
+                        tch::wait_warp(&bar_acc_empty[set], (use[set] & 1) ^ 1, a.dbg, __LINE__);
                         use[set]++;
                         tc::tc_fence_after();
                         if (lane == 0) {
                             const uint32_t d0 = tmem + set * a.set_cols;
+                            const uint32_t am = alo0 + (uint32_t)m * tile_step;
                             uint32_t acc = 0;
-                            for (int t = 0; t < st.taps; t++) {
-                                const int shift = st.taps == 9 ? (t / 3 - 1) * Wl + (t % 3 - 1) : 0;
+                            if (st.taps == 9) {
+#pragma unroll
+                                for (int t = 0; t < 9; t++) {
+                                    const uint32_t at = am + (uint32_t)(((t / 3 - 1) * Wl + (t % 3 - 1)) * (int)rowq);
+                                    const uint32_t bt = wplo0 + (uint32_t)t * tapb;
+                                    for (int k = 0; k < nk; k++) {
+                                        tch::mma_ss(d0, at + (uint32_t)(k / kpr) * slabq + (uint32_t)(k % kpr) * 2u, ahi, bt + (uint32_t)(2 * k * st.N), bhi, idescN, acc);
+                                        acc = 1;
+                                    }
+                                }
+                            } else {
                                 for (int k = 0; k < nk; k++) {
-                                    const uint64_t ad = tch::sw_desc(in_addr + (k / kpr) * BI.slab_stride + (k % kpr) * 32 + (uint32_t)(pos0 + m * 128 + shift) * BI.row, BI.row);
+                                    const uint32_t ak = am + (uint32_t)(k / kpr) * slabq + (uint32_t)(k % kpr) * 2u;
                                     for (int pc = 0; pc < pieces; pc++) {
-                                        const uint64_t bd = tc::smem_desc(wp_addr + pc * piece_bytes + (uint32_t)(t * (st.Cin >> 3) + 2 * k) * lbo_b, lbo_b, 128);
-                                        tc::mma_f16(d0, ad, bd, idescN, acc);
+                                        tch::mma_ss(d0, ak, ahi, wplo0 + (uint32_t)pc * pieceq + (uint32_t)(2 * k * st.N), bhi, idescN, acc);
                                         acc = 1;
                                     }
                                 }
                             }
                             tc::mma_commit(&bar_acc_full[set]);
-                            if (m == ntile - 1) tc::mma_commit(&bar_wp_empty);
+                            if (m == ntile - 1 && !a.resident) tc::mma_commit(&bar_wp_empty);
                         }
                         __syncwarp();
                     }
@@ -412,7 +479,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
         const int etid = tid - 64;                              // 0..255 over both warpgroups
         const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
         const float *s_bias = reinterpret_cast<const float *>(smem + a.bias_smem);
-        tch::wait(&bar_bias, 0, a.dbg, __LINE__);
+        tch::wait_warp(&bar_bias, 0, a.dbg, __LINE__);
         pdl_wait();
         unsigned g = 0, sc = 0, ca[2] = {0, 0}, cd[2] = {0, 0};
         for (int tile = blockIdx.x, it = 0; tile < a.ntiles; tile += gridDim.x, it++) {
@@ -421,7 +488,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
             if (a.merge_C) {
                 // ---- FPN merge: buffer 0 (lateral) += crop(deconv_k4s2p1(coarse)) at in-image positions; packed HFMA2, the
                 //      sum of <= 5 terms is stored as FP16 anyway (same operation order as k_fpn_merge_h2)
-                tch::wait(&bar_in, it & 1, a.dbg, __LINE__);
+                tch::wait_warp(&bar_in, it & 1, a.dbg, __LINE__);
                 const TchBuf &B0 = a.buf[0], &BM = a.buf[a.merge_buf];
                 const int UH = a.H >> 1, UW = a.W >> 1, CW = UW + 2;
                 const int cy0 = ((Y0 + B0.rows_lo + 1) >> 1) - 1;
@@ -432,7 +499,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                     const int ly = p / Wl, lx = p - ly * Wl;
                     const int y = Y0 + B0.rows_lo + ly, x = lx - 1;
                     if (x < 0 || x >= a.W || y < 0 || y >= a.H) continue;
-                    unsigned char *slot = smem + B0.off + tch::chunk_off(128, a.slack + p, j);
+                    unsigned char *slot = smem + B0.off + tch::chunk_off(128, B0.slack + p, j);
                     uint4 accv = *reinterpret_cast<const uint4 *>(slot);
                     __half2 *acc = reinterpret_cast<__half2 *>(&accv);
                     const int i_hi = (y + 1) >> 1, j_hi = (x + 1) >> 1;
@@ -462,7 +529,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                 const TchStage &st = a.st[s];
                 const int npos = st.nrows * Wl, ntile = (npos + 127) >> 7;
                 // a warp with no tile in this stage must not arrive for stage sc before phase sc-1 of bar_stage has completed
-                if (sc > 0) tch::wait(&bar_stage, (sc - 1) & 1, a.dbg, __LINE__);
+                if (sc > 0) tch::wait_warp(&bar_stage, (sc - 1) & 1, a.dbg, __LINE__);
                 for (int m = 0; m < ntile; m++) {
                     const int set = a.nsets == 2 ? ((g + m) & 1) : 0;
                     const unsigned pa = ca[set] & 1, pd = cd[set] & 1;
@@ -479,7 +546,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                     uint32_t acc_col = 0;
                     if (st.type == TCH_DWPW) {
                         // ---- mid-epilogue: depthwise accumulators -> + bias, ReLU -> packed FP16, back into TMEM in place
-                        tch::wait(&bar_dw_full[set], pd, a.dbg, __LINE__);
+                        tch::wait_warp(&bar_dw_full[set], pd, a.dbg, __LINE__);
                         tc::tc_fence_after();
                         const float *bd = s_bias + st.bias_dw;
                         for (int k = 0; k < (st.Cin >> 4); k++) {
@@ -500,7 +567,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                         if (lane == 0) tch::mbar_arrive(&bar_a16_full[set]);
                         acc_col = st.Cin;
                     }
-                    tch::wait(&bar_acc_full[set], pa, a.dbg, __LINE__);
+                    tch::wait_warp(&bar_acc_full[set], pa, a.dbg, __LINE__);
                     tc::tc_fence_after();
                     const float *bp = s_bias + st.bias_pw;
                     if (st.type != TCH_HEAD) {
@@ -520,7 +587,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                                     if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
                                     pk[i] = inimg ? tch::pack_h2(f0, f1) : 0u;
                                 }
-                                const int p = a.slack + prow * Wl + lx;
+                                const int p = BO.slack + prow * Wl + lx;
                                 const int c16 = st.ob_c16[jb];
                                 unsigned char *base = smem + BO.off + (c16 >> 2) * BO.slab_stride;
                                 const int j0 = (c16 & 3) * 2;
@@ -591,7 +658,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                     __threadfence();
                     NmsSmem &S = *reinterpret_cast<NmsSmem *>(smem + a.head.nms_smem);
                     int *s_kept = reinterpret_cast<int *>(smem + a.head.nms_smem + ((sizeof(NmsSmem) + 15) & ~15));
-                    nms_image<TCH_EPI_THREADS, true>(b, etid, a.head.params->nms_thr, a.head.pb, S, s_kept, [] { tch::epi_bar(); });
+                    nms_image<TCH_EPI_THREADS, true>(b, etid, a.head.params->nms_thr, a.head.params, a.head.pb, S, s_kept, [] { tch::epi_bar(); });
                     if (etid == 0) a.head.done[b] = 0;           // self-cleaning for the next forward
                 }
             }

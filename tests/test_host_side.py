@@ -154,3 +154,42 @@ int main() {
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-I", csrc, str(src), "-o", str(exe)])
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "pool ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_capacity_guard_for_32bit_activation_offsets(built_lib):
+    """the kernels index activations with 32-bit element offsets; rf_create must refuse a max_batch whose largest
+    tensor (the stem output, H/2 x W/2 x 16) does not fit, with RF_ERR_CAPACITY, before any device work."""
+    from retinaface_b200 import Engine, RfError
+    with pytest.raises(RfError) as e:
+        Engine(caffemodel("mnet25"), 896, 1280, max_batch=468)      # 468 * 448 * 640 * 16 = 2,146,959,360... just below: see next
+    # 468 images: 468 * 448 * 640 * 16 = 2,146,959,360 < 2^31 - 1 = 2,147,483,647 -> accepted by the guard (then fails later without a GPU)
+    assert e.value.status in (-5, -4) or e.value.status == -6
+    with pytest.raises(RfError) as e:
+        Engine(caffemodel("mnet25"), 896, 1280, max_batch=469)
+    assert e.value.status == -6 and "32-bit" in str(e.value)
+    with pytest.raises(RfError) as e:
+        Engine(caffemodel("mnet25"), 448, 448, max_batch=2676)
+    assert e.value.status == -6
+
+
+def test_tile_plan_of_the_headline_config(built_lib):
+    """rf_plan_describe (host-only): the FP16 plan of BASELINE configs[1] runs as persistent tile chains -- at most 15 kernel
+    launches per forward, every chain within the 227 KB shared-memory / 512-column TMEM budget of an SM -- and falls back
+    to the round-1 kernels layer by layer where a chain cannot fit (wide maps); RF_FLAG_LEGACY_TC restores one kernel per layer."""
+    from retinaface_b200.capi import RF_FLAG_LEGACY_TC, plan_describe
+    text = plan_describe(caffemodel("mnet25"), 448, 448, max_batch=8)
+    launches = int(text.split()[0])
+    assert launches <= 15, text
+    chains = [ln for ln in text.splitlines() if ln.startswith("tile_")]
+    assert len(chains) >= 8
+    assert any("heads+decode" in ln for ln in chains) and any("merge+aggr" in ln for ln in chains)
+    for ln in chains:
+        smem = int(re.search(r"smem (\d+) B", ln).group(1))
+        sets, cols = (int(x) for x in re.search(r"TMEM (\d+) x (\d+) cols", ln).groups())
+        assert smem <= 227 * 1024 and sets * cols <= 512, ln
+    legacy = plan_describe(caffemodel("mnet25"), 448, 448, max_batch=8, flags=RF_FLAG_LEGACY_TC)
+    assert int(legacy.split()[0]) == 30 and "tile_" not in legacy
+    big = plan_describe(caffemodel("mnet25"), 896, 1280, max_batch=8)
+    assert int(big.split()[0]) <= 30 and "tc2d_dw3" in big          # the 640-wide level does not fit a chain
+    for hw in ((288, 416), (320, 320), (96, 160)):
+        assert int(plan_describe(caffemodel("mnet-deconv-0517"), hw[0], hw[1], max_batch=3).split()[0]) <= 30

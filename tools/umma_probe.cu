@@ -237,6 +237,30 @@ __global__ void __launch_bounds__(128) k_probe(const __grid_constant__ CUtensorM
     if (warp == 1) tc::tmem_dealloc<512>(tmem);
 }
 
+struct StoreMaps { CUtensorMap in; CUtensorMap st[3]; };
+// loads a box with maps.in and stores it back through maps.st[idx] at (0, sx, sy, b)
+__global__ void __launch_bounds__(128) k_store_probe(const __grid_constant__ StoreMaps maps, int idx, int lx, int ly, int sx, int sy, int b, unsigned bytes) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tc::mbar_expect_tx(&bar, bytes);
+        tma_load_4d(smem, &maps.in, &bar, 0, lx, ly, b);
+    }
+    __syncthreads();
+    tc::mbar_wait(&bar, 0);
+    tc::fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(&maps.st[idx]), "r"(tc::smem_u32(smem)), "r"(0), "r"(sx), "r"(sy), "r"(b) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
 static float h2f(__half h) { return __half2float(h); }
 
 int main(int argc, char **argv) {
@@ -376,6 +400,34 @@ int main(int argc, char **argv) {
             bad += got != want;
         }
         printf("s2: elementStrides {1,2,2,1}, hypothesis box(lx,ly) <- (x0+2lx, y0+2ly): mismatches %ld of %d\n", bad, 64 * C);
+        return bad ? 1 : 0;
+    }
+    if (test == "store") {
+        // variant 0: in-bounds box; 1: box starting at x = -1 (pad column) and hanging over the bottom edge
+        __half *dout;
+        CKC(cudaMalloc(&dout, hin.size() * 2));
+        CKC(cudaMemset(dout, 0, hin.size() * 2));
+        StoreMaps sm;
+        // variants: 0 in bounds; 1 in bounds, runtime map index 2; 2 box hangs over right + bottom edge; 3 box starts at x = -1
+        const int sbw = 16, sbh = 4;
+        sm.in = make_map(din, C, W, H, B, C, sbw, sbh, sw);
+        for (int i = 0; i < 3; i++) sm.st[i] = make_map(dout, C, W, H, B, C, sbw, sbh, sw);
+        const int lx = variant == 3 ? -1 : (variant == 2 ? 20 : 4), ly = variant == 2 ? 26 : 8;
+        CKC(cudaFuncSetAttribute(k_store_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        k_store_probe<<<1, 128, 64 * 1024>>>(sm, variant == 1 ? 2 : 0, lx, ly, lx, ly, 1, (unsigned)(sbw * sbh * C * 2));
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("store variant %d: FAILED: %s\n", variant, cudaGetErrorString(e)); return 1; }
+        std::vector<__half> ho(hin.size());
+        CKC(cudaMemcpy(ho.data(), dout, ho.size() * 2, cudaMemcpyDeviceToHost));
+        long bad = 0, wrote = 0;
+        for (int b = 0; b < B; b++) for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) for (int c = 0; c < C; c++) {
+            const size_t i = (((size_t)b * H + y) * W + x) * C + c;
+            const bool inbox = b == 1 && x >= lx && x < lx + sbw && y >= ly && y < ly + sbh;   // (x, y range over the tensor: out-of-bounds box parts never count)
+            const float want = inbox ? h2f(hin[i]) : 0.f;
+            bad += h2f(ho[i]) != want;
+            wrote += inbox;
+        }
+        printf("store variant %d: box at (%d,%d) %dx%d: mismatches %ld (box elements in bounds %ld)\n", variant, lx, ly, sbw, sbh, bad, wrote);
         return bad ? 1 : 0;
     }
     printf("unknown test %s\n", test.c_str());
