@@ -1034,6 +1034,8 @@ int rf_profile_layers(rf_handle h, int n, int iters, char (*names)[64], float *m
         set_params(h, h->cur_thr, h->cur_nms);
         run_steps(h, n, h->stream, false);  // warm everything once (also leaves consistent inputs for every step)
         CK(cudaStreamSynchronize(h->stream));
+        struct ProfGuard { rf_handle h; ~ProfGuard() { h->profiling = false; } } guard{h};
+        h->profiling = true;
         for (size_t si = 0; si < h->steps.size(); si++) {
             auto &st = h->steps[si];
             if (cnt >= cap) break;

@@ -334,10 +334,12 @@ void plan_heads_and_nms(Builder &B, bool with_heads, bool with_nms) {
         s.launch = [=](int n, cudaStream_t st) {
             const T *feat[3] = {T_(f0), T_(f1), T_(f2)};
             HeadWeights hws[3] = {{Wd(w0), Wd(b0), 1.f}, {Wd(w1), Wd(b1), 1.f}, {Wd(w2), Wd(b2), 1.f}};
-            launch_head_decode<T>(feat, hws, h->lv, n, W, H, h->d_params, h->pb, h->blobs_in_plan ? h->d_blobs : nullptr, st);
+            launch_head_decode<T>(feat, hws, h->lv, n, W, H, h->d_params, h->pb, h->blobs_in_plan ? h->d_blobs : nullptr, st, with_nms);
         };
+        if (with_nms) s.name = "heads_1x1+softmax+decode+nms_all_levels";     // decode -> NMS in one launch (last block per image)
         h->head_step = (int)h->steps.size();
         B.step(std::move(s));
+        if (with_nms) return;
     }
     if (with_nms) {
         Step s;

@@ -127,7 +127,7 @@ void build_plan_i8(rf_handle h) {
     auto Wd = [h](size_t off) { return h->d_weights + off; };
     auto scale_of = [h](const std::string &name) -> float {
         auto it = h->int8_scales.find(name);
-        if (it == h->int8_scales.end()) { h->err = "INT8 calibration table lacks the scale of tensor '" + name + "'"; throw CudaFail{cudaErrorInvalidValue, "INT8 calibration table lookup", __FILE__, __LINE__}; }
+        if (it == h->int8_scales.end()) throw PlanFail{RF_ERR_MODEL, "INT8 calibration table lacks the scale of tensor '" + name + "'"};
         return it->second;
     };
     auto tscale = [&](int id) { return scale_of(h->tensors[id].name); };
@@ -185,7 +185,7 @@ void build_plan_i8(rf_handle h) {
             for (int t = 0; t < 9; t++) wd[t * C + c] = dw.w[(size_t)c * 9 + t] * s_in;     // float32 product, as the oracle
         size_t owd = B.add_weights(wd), obd = B.add_weights(dw.b);
         const DwGeom geo = dw_geometry_i8(C, N, ih, iw, S);
-        if (geo.rows == 0) throw CudaFail{cudaErrorInvalidConfiguration, "dw_geometry_i8: layer does not fit shared memory", __FILE__, __LINE__};
+        if (geo.rows == 0) throw PlanFail{RF_ERR_UNSUPPORTED, fmt("INT8 layer mobilenet0_conv%d (%dx%d, %d channels) does not fit shared memory", i, iw, ih, C)};
         int tin = cur;
         int tpw = B.tensor("mobilenet0_relu" + std::to_string(i + 1) + "_fwd", oh, ow_, N);
         const int Kpad = (C + 31) / 32 * 32;
@@ -360,15 +360,10 @@ void build_plan_i8(rf_handle h) {
         s.launch = [=](int n, cudaStream_t st) {
             const int8_t *feat[3] = {Q_(f0), Q_(f1), Q_(f2)};
             HeadWeights hws[3] = {{Wd(w0), Wd(b0), s0}, {Wd(w1), Wd(b1), s1}, {Wd(w2), Wd(b2), s2}};
-            launch_head_decode<int8_t>(feat, hws, h->lv, n, W, H, h->d_params, h->pb, h->blobs_in_plan ? h->d_blobs : nullptr, st);
+            launch_head_decode<int8_t>(feat, hws, h->lv, n, W, H, h->d_params, h->pb, h->blobs_in_plan ? h->d_blobs : nullptr, st, true);
         };
+        s.name = "i8_heads_1x1+softmax+decode+nms_all_levels";      // decode -> NMS in one launch (last block per image)
         h->head_step = (int)h->steps.size();
-        B.step(std::move(s));
-    }
-    {
-        Step s;
-        s.name = "sort+nms";
-        s.launch = [=](int n, cudaStream_t st) { launch_nms(n, h->d_params, h->pb, st); };
         B.step(std::move(s));
     }
 }

@@ -357,7 +357,9 @@ bool choose_tile(rf_handle h, TileChain &c, int max_batch, int max_faces, int fo
         for (int res = allow_res ? 1 : 0; res >= 0; res--) {
             if (!finalize_chain(h, c, th, max_faces, res != 0)) continue;
             const long tiles = (long)max_batch * c.args.tiles_per_img;
-            const double waves = std::ceil((double)tiles / 148.0);
+            // two CTAs share an SM when shared memory (and TMEM: 512 columns) allows: they fill each other's hand-off gaps
+            const int occ = (2 * (c.args.smem_bytes + 1024) <= 232448 && 2 * tch_tmem_cols(c.args.nsets * c.args.set_cols) <= 512) ? 2 : 1;
+            const double waves = std::ceil((double)tiles / (148.0 * (occ == 2 ? 1.6 : 1.0)));
             // MMA tiles + per-stage hand-offs (streamed weights: one exposed load per stage) + per-tile set-up
             const double cost = waves * (c.mtiles + (res ? 1.0 : 4.0) * c.stages.size() + 4.0);
             if (cost < best || (cost == best && th > best_th)) { best = cost; best_th = th; best_res = res != 0; }
@@ -391,6 +393,27 @@ void launch_chain(rf_handle h, const std::shared_ptr<TileChain> &cp, int n, cuda
     a.nimg = n;
     a.ntiles = n * a.tiles_per_img;
     a.dbg = h->tile_dbg_dev;
+    a.trace = nullptr;
+#ifdef RF_TCH_TRACE
+    {   // one trace buffer per chain (host-mapped), reset at every launch: holds the LAST launch's timeline of CTA 0
+        static std::map<const TileChain *, unsigned long long *> bufs;
+        auto it = bufs.find(&c);
+        if (it == bufs.end()) {
+            unsigned long long *p = nullptr;
+            CK(cudaHostAlloc(&p, 8 * 1024, cudaHostAllocMapped));
+            it = bufs.emplace(&c, p).first;
+        }
+        CK(cudaStreamSynchronize(st));
+        if (it->second[0]) {
+            const unsigned n = (unsigned)std::min<unsigned long long>(it->second[0], 500);
+            fprintf(stderr, "TRACE %s:", c.name.c_str());
+            for (unsigned i = 0; i < n; i++) fprintf(stderr, " %llu@%llu", it->second[1 + 2 * i], it->second[2 + 2 * i] - it->second[2]);
+            fprintf(stderr, "\n");
+        }
+        memset(it->second, 0, 8 * 1024);
+        a.trace = it->second;
+    }
+#endif
     a.warena = reinterpret_cast<const unsigned char *>(h->d_weights_h);
     a.bias = h->d_weights + c.bias_off;
     TchMaps maps;
@@ -407,7 +430,7 @@ void launch_chain(rf_handle h, const std::shared_ptr<TileChain> &cp, int n, cuda
         a.head.params = h->d_params;
         a.head.net_w = h->cfg.net_w; a.head.net_h = h->cfg.net_h;
         a.head.done = h->pb.tile_done;
-        a.head.expected = c.fused_nms ? h->tile_expected : 0;
+        a.head.expected = (c.fused_nms && !h->profiling) ? h->tile_expected : 0;    // rf_profile_layers launches single steps: no last-block NMS then
         for (int k = 0; k < 3; k++) a.head.blobs[k] = h->blobs_in_plan ? h->d_blobs[3 * c.level + k] : nullptr;
     }
     const int grid = std::min(a.ntiles, 148);
@@ -460,8 +483,14 @@ cudaError_t tile_init() {
     return cudaFuncSetAttribute(k_tile_chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCH_SMEM_LIMIT);
 }
 
-// RF_TILE_MASK bits: which parts of the FP16 plan run as tile chains (default all); the others use the round-1 kernels
-enum { TM_A = 1, TM_B = 2, TM_CD = 4, TM_E = 8, TM_AGGR = 16, TM_SSH = 32, TM_HEAD = 64, TM_NMS = 128 };
+// RF_TILE_MASK bits: which parts of the FP16 plan run as tile chains; the others use the round-1 kernels.
+enum { TM_A = 1, TM_B = 2, TM_C = 4, TM_D = 8, TM_E = 16, TM_AGGR = 32, TM_SSH = 64, TM_HEAD = 128, TM_NMS = 256, TM_ALL = 511 };
+// Measured on a B200 (profiles/README.md, tools/mask_sweep.py): with ONE execution context (a single forward at a time: the
+// blocking / latency mode) the convolution chains + chain B shorten the step; with several contexts overlapping batches
+// (throughput mode) the GPU is already kept busy by batch-level parallelism and what counts is SM-time per step, where the
+// short round-1 kernels (2-4 CTAs per SM) still win -- there only the fused decode + NMS tail is taken over.
+constexpr unsigned TM_LATENCY = TM_B | TM_AGGR | TM_SSH | TM_HEAD | TM_NMS;
+constexpr unsigned TM_THROUGHPUT = 0;
 
 // builds the plan for one mask; false: the predictors could not be fused at all three levels (the caller retries without)
 static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
@@ -529,12 +558,30 @@ static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
             }
         }
     };
-    backbone("A", {3, 5}, mask & TM_A, nullptr, nullptr, 0);
-    backbone("B", {7, 9}, mask & TM_B, "rf_c1_red_conv", &lat1, 1);
+    // RF_TILE_SINGLE=1: one chain per depthwise+pointwise pair (no halo recomputation between layers; more, smaller kernels)
+    const bool single = env_int("RF_TILE_SINGLE", 0) != 0;
+    if (single) {
+        backbone("A3", {3}, mask & TM_A, nullptr, nullptr, 0);
+        backbone("A5", {5}, mask & TM_A, nullptr, nullptr, 0);
+        backbone("B7", {7}, mask & TM_B, nullptr, nullptr, 0);
+        backbone("B9", {9}, mask & TM_B, "rf_c1_red_conv", &lat1, 1);
+    } else {
+        backbone("A", {3, 5}, mask & TM_A, nullptr, nullptr, 0);
+        backbone("B", {7, 9}, mask & TM_B, "rf_c1_red_conv", &lat1, 1);
+    }
     c1 = cur;
     const int h8 = cur_h, w8 = cur_w;
-    backbone("C", {11, 13, 15}, mask & TM_CD, nullptr, nullptr, 0);
-    backbone("D", {17, 19, 21}, mask & TM_CD, "rf_c2_lateral", &lat2, 2);
+    if (single) {
+        backbone("C11", {11}, mask & TM_C, nullptr, nullptr, 0);
+        backbone("C13", {13}, mask & TM_C, nullptr, nullptr, 0);
+        backbone("C15", {15}, mask & TM_C, nullptr, nullptr, 0);
+        backbone("D17", {17}, mask & TM_D, nullptr, nullptr, 0);
+        backbone("D19", {19}, mask & TM_D, nullptr, nullptr, 0);
+        backbone("D21", {21}, mask & TM_D, "rf_c2_lateral", &lat2, 2);
+    } else {
+        backbone("C", {11, 13, 15}, mask & TM_C, nullptr, nullptr, 0);
+        backbone("D", {17, 19, 21}, mask & TM_D, "rf_c2_lateral", &lat2, 2);
+    }
     c2 = cur;
     const int h16 = cur_h, w16 = cur_w;
     backbone("E", {23}, mask & TM_E, nullptr, nullptr, 0);
@@ -605,10 +652,10 @@ static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
             int bcat = add_buf(*c, 64, true, cat);
             int bctx1 = add_buf(*c, 16);
             int bctx31 = add_buf(*c, 16);
-            add_conv(*c, bi, {&m.conv(p + "_conv1")}, {{bcat, 0, 1}});
-            add_conv(*c, bi, {&m.conv(p + "_context_conv1")}, {{bctx1, 0, 1}});
-            add_conv(*c, bctx1, {&m.conv(p + "_context_conv2")}, {{bcat, 32, 1}});
-            add_conv(*c, bctx1, {&m.conv(p + "_context_conv3_1")}, {{bctx31, 0, 1}});
+            // branches that share an input run as ONE stage over the rows the neediest branch wants: an MMA's time is its A-operand
+            // read from shared memory (128 rows x 32 bytes whatever N), so the other branch's output columns ride along for free
+            add_conv(*c, bi, {&m.conv(p + "_conv1"), &m.conv(p + "_context_conv1")}, {{bcat, 0, 1}, {bctx1, 0, 1}});
+            add_conv(*c, bctx1, {&m.conv(p + "_context_conv2"), &m.conv(p + "_context_conv3_1")}, {{bcat, 32, 1}, {bctx31, 0, 1}});
             add_conv(*c, bctx31, {&m.conv(p + "_context_conv3_2")}, {{bcat, 48, 1}});
             if (mask & TM_HEAD) {
                 const int strides[3] = {32, 16, 8};
@@ -655,7 +702,7 @@ static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
 }
 
 void build_plan_tiles(rf_handle h) {
-    const unsigned mask = (unsigned)env_int("RF_TILE_MASK", 0xff);
+    const unsigned mask = (unsigned)env_int("RF_TILE_MASK", (int)(h->cfg.streams == 1 ? TM_LATENCY : TM_THROUGHPUT));
     for (unsigned m : {mask, mask & ~(unsigned)(TM_HEAD | TM_NMS)}) {
         // a failed attempt leaves no trace
         h->steps.clear(); h->tensors.clear(); h->tensor_by_name.clear(); h->chains.clear();

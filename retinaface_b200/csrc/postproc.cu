@@ -36,9 +36,10 @@ struct HeadLaunch {
 // exactly one level's 32x64 predictor weights.
 template <typename T, bool WRITE_BLOBS>
 __global__ void __launch_bounds__(128) k_head_decode(HeadLaunch L, int net_w, int net_h,
-                                                     const PostParams *__restrict__ params, PostBuffers pb) {
+                                                     const PostParams *__restrict__ params, PostBuffers pb, int fuse_nms) {
     __shared__ __align__(16) float sw[32 * 64];
     __shared__ float sb[32];
+    __shared__ int s_last;
     const int blk = blockIdx.x;
     const int l = blk >= L.blk_base[2] ? 2 : (blk >= L.blk_base[1] ? 1 : 0);
     const LevelDesc lv = L.lv[l];
@@ -49,8 +50,8 @@ __global__ void __launch_bounds__(128) k_head_decode(HeadLaunch L, int net_w, in
     pdl_wait();
     const int hw = lv.h * lv.w;
     const int j = (blk - L.blk_base[l]) * blockDim.x + threadIdx.x;
-    if (j >= hw) return;
     const int img = blockIdx.y;
+    if (j < hw) {
     const float thr = params->score_thr;
     const T *f = reinterpret_cast<const T *>(L.feat[l]) + ((size_t)img * hw + j) * 64;
     float x[64];
@@ -111,6 +112,22 @@ __global__ void __launch_bounds__(128) k_head_decode(HeadLaunch L, int net_w, in
             rf_det d;
             decode_one(pf[a], reg, lm, lv, a, ih, iw, net_w, net_h, lv.anchor_base + a * hw + j, d);
             append_candidate(pb, img, d);
+        }
+    }
+    }
+    if (fuse_nms) {
+        // decode -> NMS in ONE launch: the block that finishes an image's last pixels sorts and suppresses it (last-block pattern;
+        // the counter cleans itself for the next forward)
+        __shared__ NmsSmem S;
+        extern __shared__ int s_kept[];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&pb.tile_done[img], 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            nms_image<128, true>(img, threadIdx.x, params->nms_thr, params, pb, S, s_kept, [] { __syncthreads(); });
+            if (threadIdx.x == 0) pb.tile_done[img] = 0;
         }
     }
 }
@@ -193,7 +210,7 @@ size_t nms_smem_bytes(int max_faces) { return sizeof(int) * (size_t)max_faces; }
 template <typename T>
 void launch_head_decode(const T *const feat[3], const HeadWeights hw[3], const LevelDesc lv[3], int n,
                         int net_w, int net_h, const PostParams *params, const PostBuffers &pb,
-                        float *const blobs[9], cudaStream_t s) {
+                        float *const blobs[9], cudaStream_t s, bool fuse_nms) {
     HeadLaunch L;
     int blk = 0;
     bool write = blobs && blobs[0];
@@ -207,15 +224,16 @@ void launch_head_decode(const T *const feat[3], const HeadWeights hw[3], const L
     L.blk_base[3] = blk;
     for (int i = 0; i < 9; i++) L.blobs[i] = write ? blobs[i] : nullptr;
     dim3 grid(blk, n);
-    if (write) launch_k(k_head_decode<T, true>, grid, dim3(128), 0, s, L, net_w, net_h, params, pb);
-    else launch_k(k_head_decode<T, false>, grid, dim3(128), 0, s, L, net_w, net_h, params, pb);
+    const size_t dyn = fuse_nms ? nms_smem_bytes(pb.max_faces) : 0;
+    if (write) launch_k(k_head_decode<T, true>, grid, dim3(128), dyn, s, L, net_w, net_h, params, pb, fuse_nms ? 1 : 0);
+    else launch_k(k_head_decode<T, false>, grid, dim3(128), dyn, s, L, net_w, net_h, params, pb, fuse_nms ? 1 : 0);
 }
 template void launch_head_decode<float>(const float *const[3], const HeadWeights[3], const LevelDesc[3], int, int, int,
-                                        const PostParams *, const PostBuffers &, float *const[9], cudaStream_t);
+                                        const PostParams *, const PostBuffers &, float *const[9], cudaStream_t, bool);
 template void launch_head_decode<__half>(const __half *const[3], const HeadWeights[3], const LevelDesc[3], int, int, int,
-                                         const PostParams *, const PostBuffers &, float *const[9], cudaStream_t);
+                                         const PostParams *, const PostBuffers &, float *const[9], cudaStream_t, bool);
 template void launch_head_decode<int8_t>(const int8_t *const[3], const HeadWeights[3], const LevelDesc[3], int, int, int,
-                                         const PostParams *, const PostBuffers &, float *const[9], cudaStream_t);
+                                         const PostParams *, const PostBuffers &, float *const[9], cudaStream_t, bool);
 
 void launch_blob_decode(const float *const blobs[9], const LevelDesc lv[3], int n, int net_w, int net_h,
                         const PostParams *params, const PostBuffers &pb, cudaStream_t s) {
@@ -237,7 +255,12 @@ void launch_merge_views(const PostBuffers &src, const ViewSet &vs, const PostBuf
 
 cudaError_t postproc_init() {
     // static 27 KB + up to 32 KB dynamic (max_faces <= 8192) exceeds the 48 KB default: opt in once
-    return cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes(8192));
+    cudaError_t e;
+    const int dyn = (int)nms_smem_bytes(8192);
+#define RF_HD_ATTR(T_, W_) if ((e = cudaFuncSetAttribute(k_head_decode<T_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn))) return e
+    RF_HD_ATTR(float, true); RF_HD_ATTR(float, false); RF_HD_ATTR(__half, true); RF_HD_ATTR(__half, false); RF_HD_ATTR(int8_t, true); RF_HD_ATTR(int8_t, false);
+#undef RF_HD_ATTR
+    return cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
 }
 
 }  // namespace rf

@@ -39,6 +39,7 @@ struct HeadWeights {
     float in_scale;     // 1 for float/half features; the concat tensor's quantisation scale for int8 features
 };
 
+// fuse_nms: the block that completes an image also sorts + suppresses it (decode -> NMS in one launch; pb.tile_done counts).
 // Fused per-level predictor + decode: 1x1 convs (cls 4, bbox 8, landmark 20), the 2-way softmax,
 // threshold, anchor decode, clip -> candidate append.  One launch covers all three levels.
 // feat[l]: NHWC [n][h][w][64] SSH output (post concat+ReLU) in T.  blobs (optional, may be all
@@ -46,7 +47,7 @@ struct HeadWeights {
 template <typename T>
 void launch_head_decode(const T *const feat[3], const HeadWeights hw[3], const LevelDesc lv[3], int n,
                         int net_w, int net_h, const PostParams *params, const PostBuffers &pb,
-                        float *const blobs[9], cudaStream_t s);
+                        float *const blobs[9], cudaStream_t s, bool fuse_nms = false);
 
 // Decode from caller-provided head blobs (device, NCHW f32, engine order): rf_postprocess.
 void launch_blob_decode(const float *const blobs[9], const LevelDesc lv[3], int n, int net_w, int net_h,

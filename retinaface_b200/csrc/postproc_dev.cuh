@@ -110,6 +110,7 @@ __device__ __forceinline__ void nms_image(int img, int tid, float thr, const Pos
     const rf_det *recs = pb.cand_recs + (size_t)img * A;
     auto ldkey = [&](int i) { return ACQUIRE ? __ldcg(&gkeys[i]) : gkeys[i]; };
     auto ldbox = [&](unsigned e) {
+        e = e < (unsigned)A ? e : (unsigned)A - 1u;     // a key is always an anchor index; never index past the records whatever was read
         const float *f = reinterpret_cast<const float *>(&recs[e].face);
         return ACQUIRE ? make_float4(__ldcg(f + 1), __ldcg(f + 2), __ldcg(f + 3), __ldcg(f + 4)) : make_float4(f[1], f[2], f[3], f[4]);
     };
@@ -155,6 +156,33 @@ __device__ __forceinline__ void nms_image(int img, int tid, float thr, const Pos
         return ldbox((unsigned)(keys[i] & 0xffffffffu));
     };
     int nkept = 0;  // thread 0's running count (mirrored to S.nkept at the end)
+    if (n <= 64) {
+        // few candidates (the usual case: tens per image): the whole suppression relation at once -- thread (i, half) tests box i
+        // against 32 later boxes -> one 64-bit row per candidate; then ONE thread walks the rows.  Same greedy rule (a box is
+        // suppressed only by a KEPT earlier box), no barrier per kept face.
+        unsigned long long *rows = S.tmp;          // the rank sort is done with S.tmp
+        for (int t = tid; t < 2 * n; t += NT) {
+            const int i = t >> 1, j0 = (t & 1) * 32;
+            const float4 s = S.box[i];
+            const float area1 = __fmul_rn(__fadd_rn(__fsub_rn(s.z, s.x), 1.0f), __fadd_rn(__fsub_rn(s.w, s.y), 1.0f));
+            unsigned bits = 0;
+            for (int b = 0; b < 32; b++) {
+                const int j = j0 + b;
+                if (j > i && j < n && suppresses(s, area1, S.box[j], thr)) bits |= 1u << b;
+            }
+            reinterpret_cast<unsigned *>(rows + i)[t & 1] = bits;
+        }
+        sync();
+        if (tid == 0) {
+            unsigned long long removed = 0;
+            for (int i = 0; i < n; i++) {
+                if ((removed >> i) & 1ull) continue;
+                if (nkept < pb.max_faces) s_kept[nkept] = i;
+                nkept++;
+                removed |= rows[i];
+            }
+        }
+    } else
     for (int i = 0; i < n; i++) {
         if (flag[i]) continue;  // uniform: flags of position i are final once every earlier kept round has synchronised
         const float4 s = box_at(i);

@@ -94,6 +94,7 @@ struct TchArgs {
     int resident;             // 1: the weights of ALL stages stay in shared memory for the CTA's lifetime (loaded once, before
                               // griddepcontrol.wait); 0: streamed per stage through the wd / wp buffers
     unsigned *dbg;            // host-mapped word: code of the hand-off a timed-out wait was stuck on (0: none)
+    unsigned long long *trace;   // -DRF_TCH_TRACE builds: timeline of CTA 0 (count, then (code, ns) pairs)
     const unsigned char *warena;
     const float *bias;
     int bias_floats;
@@ -147,6 +148,27 @@ __device__ __forceinline__ void wait_warp(uint64_t *bar, unsigned parity, unsign
     wait(bar, parity, dbg, code);
     __syncwarp();
 }
+// Optional timeline of CTA 0 (build with -DRF_TCH_TRACE; tools/tile_bringup.py --trace): (event code, globaltimer ns) pairs
+#ifdef RF_TCH_TRACE
+__device__ __forceinline__ void trace(unsigned long long *t, unsigned code) {
+    if (t && blockIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        const unsigned i = atomicAdd(reinterpret_cast<unsigned *>(t), 1u);
+        if (i < 500) { t[1 + 2 * i] = code; t[2 + 2 * i] = now; }
+    }
+}
+#define TCH_TRACE(code) tch::trace(a.trace, (code))
+#else
+#define TCH_TRACE(code)
+#endif
+// one lane of a converged warp (elect.sync): ptxas then knows the guarded region runs with a single active thread and moves
+// the MMA operands to uniform registers without a waterfall loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -199,6 +221,86 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_
         ::"r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The issuing thread runs DEPENDENT scalar instructions at ~5 cycles each (tools/umma_probe.cu "rate": a loop that computes its
+// descriptors per MMA issues one MMA per ~200 cycles, whatever N): the issue blocks below are fully unrolled over taps and K
+// steps with every operand offset precomputed, so that each MMA costs two independent adds and the instruction itself.
+template <bool ACC>
+__device__ __forceinline__ void mma_ss_c(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.eq.u32 p, 0, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.u32 p, 0, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void mma_ts_c(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\tsetp.eq.u32 p, 0, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.u32 p, 0, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc) : "memory");
+}
+// operand geometry of one stage, in 16-byte units (see the MMA issuer)
+struct IssueGeo {
+    uint32_t ahi, bhi, slabq, idesc;
+    int lkpr, kpr;
+};
+// 3x3 convolution: 9 taps x NK K-steps into one accumulator; B image tap-major: tap t at t * tapb, K-step k at k * kb
+template <int NK>
+__device__ __forceinline__ void issue_conv9(uint32_t d0, uint32_t am, const uint32_t (&tapq)[9], uint32_t wplo0, uint32_t tapb, uint32_t kb, const IssueGeo &g) {
+    uint32_t ka[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) ka[k] = (uint32_t)(k >> g.lkpr) * g.slabq + (uint32_t)(k & (g.kpr - 1)) * 2u;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+        const uint32_t at = am + tapq[t], bt = wplo0 + (uint32_t)t * tapb;
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            if (t == 0 && k == 0) mma_ss_c<false>(d0, at + ka[k], g.ahi, bt + (uint32_t)k * kb, g.bhi, g.idesc);
+            else mma_ss_c<true>(d0, at + ka[k], g.ahi, bt + (uint32_t)k * kb, g.bhi, g.idesc);
+        }
+    }
+}
+// 1x1 convolution / predictors: NK K-steps x PIECES weight pieces (hi, lo) into one accumulator
+template <int NK, int PIECES>
+__device__ __forceinline__ void issue_conv1(uint32_t d0, uint32_t am, uint32_t wplo0, uint32_t pieceq, uint32_t kb, const IssueGeo &g) {
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        const uint32_t ak = am + (uint32_t)(k >> g.lkpr) * g.slabq + (uint32_t)(k & (g.kpr - 1)) * 2u;
+#pragma unroll
+        for (int pc = 0; pc < PIECES; pc++) {
+            if (k == 0 && pc == 0) mma_ss_c<false>(d0, ak, g.ahi, wplo0 + (uint32_t)pc * pieceq + (uint32_t)k * kb, g.bhi, g.idesc);
+            else mma_ss_c<true>(d0, ak, g.ahi, wplo0 + (uint32_t)pc * pieceq + (uint32_t)k * kb, g.bhi, g.idesc);
+        }
+    }
+}
+// depthwise: tap-major so that consecutive MMAs accumulate into DIFFERENT 16-column slabs; diagonal tile of (t, k) at (t * nk + k) * 32
+template <int NK>
+__device__ __forceinline__ void issue_dw9(uint32_t d0, uint32_t am, const uint32_t (&tapq)[9], uint32_t wdlo0, int nk, int k0, const IssueGeo &g) {
+    uint32_t ka[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) ka[k] = (uint32_t)((k0 + k) >> g.lkpr) * g.slabq + (uint32_t)((k0 + k) & (g.kpr - 1)) * 2u;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+        const uint32_t at = am + tapq[t], bt = wdlo0 + (uint32_t)(t * nk + k0) * 32u;
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            if (t == 0) mma_ss_c<false>(d0 + (uint32_t)(k0 + k) * 16u, at + ka[k], g.ahi, bt + (uint32_t)k * 32u, g.bhi, g.idesc);
+            else mma_ss_c<true>(d0 + (uint32_t)(k0 + k) * 16u, at + ka[k], g.ahi, bt + (uint32_t)k * 32u, g.bhi, g.idesc);
+        }
+    }
+}
+// pointwise with A from TMEM: NK K-steps into one accumulator
+template <int NK>
+__device__ __forceinline__ void issue_pw_ts(uint32_t dacc, uint32_t a_tmem, uint32_t wplo0, uint32_t kb, uint32_t bhi, uint32_t idesc) {
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        if (k == 0) mma_ts_c<false>(dacc, a_tmem, wplo0, bhi, idesc);
+        else mma_ts_c<true>(dacc, a_tmem + (uint32_t)k * 8u, wplo0 + (uint32_t)k * kb, bhi, idesc);
+    }
+}
 // D[tmem] (+)= A[tmem, packed FP16] * B[smem desc]
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -238,7 +340,7 @@ __device__ __forceinline__ void tmem_dealloc_n(uint32_t addr, int cols) {
 __host__ __device__ inline int tch_tmem_cols(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512))); }
 
 template <int UNUSED>
-__global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_constant__ TchMaps maps, const __grid_constant__ TchArgs a) {
+__global__ void __launch_bounds__(TCH_THREADS, 2) k_tile_chain(const __grid_constant__ TchMaps maps, const __grid_constant__ TchArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_in, bar_bias, bar_merge, bar_stage, bar_tile;
     __shared__ __align__(8) uint64_t bar_wd_full, bar_wd_empty, bar_wp_full, bar_wp_empty;
@@ -267,6 +369,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = s_tmem;
+    if (tid == 0) TCH_TRACE(1);
 
     if (warp == 0) {
         // =========================================== TMA producer ===========================================
@@ -354,18 +457,21 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
         if (a.resident) tch::wait_warp(&bar_bias, 0, a.dbg, __LINE__);       // every stage's weights are in shared memory
         for (int tile = blockIdx.x, it = 0; tile < a.ntiles; tile += gridDim.x, it++) {
             tch::wait_warp(&bar_in, it & 1, a.dbg, __LINE__);
+            if (lane == 0) TCH_TRACE(3);
             if (a.merge_C) tch::wait_warp(&bar_merge, it & 1, a.dbg, __LINE__);
             for (int s = 0; s < a.nstages; s++, sc++) {
                 const TchStage &st = a.st[s];
                 const TchBuf &BI = a.buf[st.in_buf];
                 if (sc > 0) tch::wait_warp(&bar_stage, (sc - 1) & 1, a.dbg, __LINE__);      // inputs of this stage are in shared memory
+                if (lane == 0) TCH_TRACE(100 + s);
                 if (!a.resident) {
                     if (st.wd_bytes) { tch::wait_warp(&bar_wd_full, wdc & 1, a.dbg, __LINE__); wdc++; }
                     tch::wait_warp(&bar_wp_full, wpc & 1, a.dbg, __LINE__); wpc++;
                 }
                 tc::tc_fence_after();
                 const int npos = st.nrows * Wl, ntile = (npos + 127) >> 7;
-                const int kpr = BI.row >> 5;                             // 16-channel K steps per row
+                const int kpr = BI.row >> 5;                             // 16-channel K steps per row: 1 | 2 | 4
+                const int lkpr = kpr == 4 ? 2 : (kpr == 2 ? 1 : 0);
                 // position index (in the input buffer) of this stage's position 0
                 const int pos0 = st.type == TCH_DWPW && st.stride == 2 ? BI.slack : BI.slack + (st.rows_lo - BI.rows_lo) * Wl;
                 const uint32_t rowq = (uint32_t)BI.row >> 4;              // 16-byte units per position
@@ -393,14 +499,15 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                         tch::wait_warp(&bar_acc_empty[set], (use[set] & 1) ^ 1, a.dbg, __LINE__);
                         use[set]++;
                         tc::tc_fence_after();
-                        if (lane == 0) {
+                        if (tch::elect_one()) {
                             const uint32_t d0 = tmem + set * a.set_cols;
                             const uint32_t am = alo0 + (uint32_t)m * tile_step;
-                            for (int k = 0; k < nk; k++) {
-                                const uint32_t ak = am + (uint32_t)(k / kpr) * slabq + (uint32_t)(k % kpr) * 2u;
-                                const uint32_t bk = wdlo0 + (uint32_t)k * 32u;
-#pragma unroll
-                                for (int t = 0; t < 9; t++) tch::mma_ss(d0 + k * 16, ak + tapq[t], ahi, bk + (uint32_t)(t * nk) * 32u, bhi, idesc16, t > 0);
+                            const tch::IssueGeo geo{ahi, bhi, slabq, idesc16, lkpr, kpr};
+                            switch (nk) {
+                                case 1: tch::issue_dw9<1>(d0, am, tapq, wdlo0, nk, 0, geo); break;
+                                case 2: tch::issue_dw9<2>(d0, am, tapq, wdlo0, nk, 0, geo); break;
+                                case 4: tch::issue_dw9<4>(d0, am, tapq, wdlo0, nk, 0, geo); break;
+                                default: for (int k0 = 0; k0 < nk; k0 += 8) tch::issue_dw9<8>(d0, am, tapq, wdlo0, nk, k0, geo); break;     // nk = 8, 16
                             }
                             tc::mma_commit(&bar_dw_full[set]);
                             if (m == ntile - 1 && !a.resident) tc::mma_commit(&bar_wd_empty);
@@ -412,9 +519,16 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                         tch::wait_warp(&bar_a16_full[set], dwuse[set] & 1, a.dbg, __LINE__);
                         dwuse[set]++;
                         tc::tc_fence_after();
-                        if (lane == 0) {
+                        if (tch::elect_one()) {
                             const uint32_t d0 = tmem + set * a.set_cols;
-                            for (int k = 0; k < nk; k++) tch::mma_ts(d0 + st.Cin, d0 + k * 8, wplo0 + (uint32_t)(2 * k * st.N), bhi, idescN, k > 0);
+                            const uint32_t kb = 2u * (uint32_t)st.N;
+                            switch (nk) {
+                                case 1: tch::issue_pw_ts<1>(d0 + st.Cin, d0, wplo0, kb, bhi, idescN); break;
+                                case 2: tch::issue_pw_ts<2>(d0 + st.Cin, d0, wplo0, kb, bhi, idescN); break;
+                                case 4: tch::issue_pw_ts<4>(d0 + st.Cin, d0, wplo0, kb, bhi, idescN); break;
+                                case 8: tch::issue_pw_ts<8>(d0 + st.Cin, d0, wplo0, kb, bhi, idescN); break;
+                                default: for (int k = 0; k < nk; k++) tch::mma_ts(d0 + st.Cin, d0 + k * 8, wplo0 + (uint32_t)k * kb, bhi, idescN, k > 0); break;
+                            }
                             tc::mma_commit(&bar_acc_full[set]);
                             if (m == ntile - 1 && !a.resident) tc::mma_commit(&bar_wp_empty);
                         }
@@ -435,31 +549,37 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                     const uint32_t pieceq = ((uint32_t)st.taps * st.Cin * st.N * 2) >> 4;
                     const uint32_t wplo0 = tch::b_desc_lo(wp_addr, (uint32_t)st.N * 16);
                     const uint32_t tapb = (uint32_t)(st.Cin >> 3) * st.N;      // B image: 16-byte units per tap
+                    uint32_t tapc[9];
+#pragma unroll
+                    for (int t = 0; t < 9; t++) tapc[t] = (uint32_t)(((t / 3 - 1) * Wl + (t % 3 - 1)) * (int)rowq);
                     for (int m = 0; m < ntile; m++) {
                         const int set = a.nsets == 2 ? ((g + m) & 1) : 0;
                         tch::wait_warp(&bar_acc_empty[set], (use[set] & 1) ^ 1, a.dbg, __LINE__);
                         use[set]++;
                         tc::tc_fence_after();
-                        if (lane == 0) {
+                        if (tch::elect_one()) {
                             const uint32_t d0 = tmem + set * a.set_cols;
                             const uint32_t am = alo0 + (uint32_t)m * tile_step;
-                            uint32_t acc = 0;
+                            const tch::IssueGeo geo{ahi, bhi, slabq, idescN, lkpr, kpr};
+                            const uint32_t kb = 2u * (uint32_t)st.N;
                             if (st.taps == 9) {
-#pragma unroll
-                                for (int t = 0; t < 9; t++) {
-                                    const uint32_t at = am + (uint32_t)(((t / 3 - 1) * Wl + (t % 3 - 1)) * (int)rowq);
-                                    const uint32_t bt = wplo0 + (uint32_t)t * tapb;
-                                    for (int k = 0; k < nk; k++) {
-                                        tch::mma_ss(d0, at + (uint32_t)(k / kpr) * slabq + (uint32_t)(k % kpr) * 2u, ahi, bt + (uint32_t)(2 * k * st.N), bhi, idescN, acc);
-                                        acc = 1;
-                                    }
+                                switch (nk) {
+                                    case 1: tch::issue_conv9<1>(d0, am, tapc, wplo0, tapb, kb, geo); break;
+                                    case 2: tch::issue_conv9<2>(d0, am, tapc, wplo0, tapb, kb, geo); break;
+                                    default: tch::issue_conv9<4>(d0, am, tapc, wplo0, tapb, kb, geo); break;       // 64 input channels
                                 }
+                            } else if (pieces == 2) {
+                                tch::issue_conv1<4, 2>(d0, am, wplo0, pieceq, kb, geo);                               // predictors: 64 channels, hi + lo
                             } else {
-                                for (int k = 0; k < nk; k++) {
-                                    const uint32_t ak = am + (uint32_t)(k / kpr) * slabq + (uint32_t)(k % kpr) * 2u;
-                                    for (int pc = 0; pc < pieces; pc++) {
-                                        tch::mma_ss(d0, ak, ahi, wplo0 + (uint32_t)pc * pieceq + (uint32_t)(2 * k * st.N), bhi, idescN, acc);
-                                        acc = 1;
+                                switch (nk) {
+                                    case 4: tch::issue_conv1<4, 1>(d0, am, wplo0, pieceq, kb, geo); break;
+                                    case 8: tch::issue_conv1<8, 1>(d0, am, wplo0, pieceq, kb, geo); break;
+                                    default: {
+                                        uint32_t acc = 0;
+                                        for (int k = 0; k < nk; k++) {
+                                            tch::mma_ss(d0, am + (uint32_t)(k >> lkpr) * slabq + (uint32_t)(k & (kpr - 1)) * 2u, ahi, wplo0 + (uint32_t)k * kb, bhi, idescN, acc);
+                                            acc = 1;
+                                        }
                                     }
                                 }
                             }
@@ -470,6 +590,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
                     }
                 }
                 g += ntile;
+                if (lane == 0) TCH_TRACE(200 + s);
             }
         }
     } else {
@@ -668,6 +789,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) k_tile_chain(const __grid_cons
     }
     tc::tc_fence_before();
     __syncthreads();
+    if (tid == 0) TCH_TRACE(9);
     if (warp == 1) tch::tmem_dealloc_n(tmem, tmem_cols);
 }
 

@@ -45,9 +45,10 @@ def _match(mine, ref, iou_min=0.7):
 
 
 @pytest.mark.parametrize("hw,nb", [((448, 448), 5), ((896, 1280), 2), ((288, 416), 3)])
-@pytest.mark.parametrize("mask", [255, 127, 63, 31])
+@pytest.mark.parametrize("mask", [511, 490, 255, 127, 63])
 def test_tile_chains_equal_round1_kernels(mask, hw, nb, golden_image, monkeypatch):
-    """The tile-chain plan (RF_TILE_MASK: 255 everything; 127 stand-alone NMS; 63 stand-alone predictors + NMS; 31 round-1 SSH)
+    """The tile-chain plan (RF_TILE_MASK: 511 every chain; 490 the default selection; 255 stand-alone NMS; 127 stand-alone predictors
+    + NMS; 63 round-1 SSH)
     against one round-1 kernel per layer (RF_FLAG_LEGACY_TC): every tensor both plans materialise within 1e-2 of its max
     (depthwise weights are FP16 diagonal tiles in the chains, FP32 in the round-1 stencil), head blobs within 1e-2, and the
     SAME faces (anchor indices) within 0.25 px / 5e-3 score -- on the photo, on noise and on shifted copies."""

@@ -86,7 +86,7 @@ def child(mask, h, w, nb, model):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--child", type=int, default=None)
-    ap.add_argument("--masks", default="1,2,4,8,16,32,96,224,255")
+    ap.add_argument("--masks", default="511,490,0")
     ap.add_argument("--hw", default="448x448")
     ap.add_argument("--batch", type=int, default=3)
     ap.add_argument("--model", default="mnet25")

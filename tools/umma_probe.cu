@@ -237,6 +237,49 @@ __global__ void __launch_bounds__(128) k_probe(const __grid_constant__ CUtensorM
     if (warp == 1) tc::tmem_dealloc<512>(tmem);
 }
 
+// MMA latency / throughput: `count` MMAs (M=128, N=n, K=16, SS mode, SW128 A) issued by one thread round-robin over `nacc`
+// independent accumulators; cycles from first issue to the commit's arrival
+__global__ void __launch_bounds__(128) k_mma_rate(int n, int count, int nacc, int ts, long long *out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 64 * 1024 / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { tc::mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 1) tc::tmem_alloc<512>(&s_tmem);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_addr = tc::smem_u32(smem), b_addr = a_addr + 32 * 1024;
+        const long long t0 = clock64();
+        for (int i = 0; i < count; i++) {
+            const uint64_t ad = sw_desc(a_addr + ((i % 9) * 7 + 3) * 128 + (i % 4) * 32, 1024, 2, 0);
+            const uint64_t bd = tc::smem_desc(b_addr + (i % 8) * 1024, (uint32_t)n * 16, 128);
+            const uint32_t d = tmem + (uint32_t)(i % nacc) * (uint32_t)n;
+            if (ts) {
+                const uint32_t acc = i >= nacc;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                             ::"r"(d), "r"(tmem + 448u), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+            } else {
+                tc::mma_f16(d, ad, bd, idesc, i >= nacc);
+            }
+        }
+        const long long t1 = clock64();
+        tc::mma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+
 struct StoreMaps { CUtensorMap in; CUtensorMap st[3]; };
 // loads a box with maps.in and stores it back through maps.st[idx] at (0, sx, sy, b)
 __global__ void __launch_bounds__(128) k_store_probe(const __grid_constant__ StoreMaps maps, int idx, int lx, int ly, int sx, int sy, int b, unsigned bytes) {
@@ -401,6 +444,25 @@ int main(int argc, char **argv) {
         }
         printf("s2: elementStrides {1,2,2,1}, hypothesis box(lx,ly) <- (x0+2lx, y0+2ly): mismatches %ld of %d\n", bad, 64 * C);
         return bad ? 1 : 0;
+    }
+    if (test == "rate") {
+        long long *dout;
+        CKC(cudaMalloc(&dout, 16));
+        CKC(cudaFuncSetAttribute(k_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        for (int ts = 0; ts < 2; ts++)
+            for (int n : {16, 32, 64, 128})
+                for (int nacc : {1, 2, 3, 4, 8}) {
+                    if (nacc * n > 448) continue;
+                    const int count = 72;
+                    k_mma_rate<<<1, 128, 80 * 1024>>>(n, count, nacc, ts, dout);
+                    CKC(cudaDeviceSynchronize());
+                    k_mma_rate<<<1, 128, 80 * 1024>>>(n, count, nacc, ts, dout);
+                    CKC(cudaDeviceSynchronize());
+                    long long h2[2];
+                    CKC(cudaMemcpy(h2, dout, 16, cudaMemcpyDeviceToHost));
+                    printf("rate %s N=%3d accumulators=%d: issue %5.1f cyc/MMA, complete %6.1f cyc/MMA (%d MMAs)\n", ts ? "TS" : "SS", n, nacc, (double)h2[0] / count, (double)h2[1] / count, count);
+                }
+        return 0;
     }
     if (test == "store") {
         // variant 0: in-bounds box; 1: box starting at x = -1 (pad column) and hanging over the bottom edge
