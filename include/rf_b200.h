@@ -82,6 +82,9 @@ typedef struct rf_config {
 #define RF_FLAG_NO_TENSORCORE 0x2u  /* FP16: use the SIMT kernels for GEMM-shaped layers too (implies RF_FLAG_SIMT_STEM) */
 #define RF_FLAG_SIMT_STEM     0x4u  /* FP16 / INT8: run all three layers of the stem on CUDA cores (FP32 conv0 weights) */
 #define RF_FLAG_DW_1D         0x8u  /* FP16 / INT8: linear (1-D) tiles for every depthwise+pointwise layer, also on large maps */
+#define RF_FLAG_NPP_RESIZE    0x20u /* letter-box with the reference's NPP branch semantics (USE_NPP: nppiResizeSqrPixel_8u_C3R,
+                                       NPPI_INTER_SUPER, resizeconvertion.cu:279-316) -- coverage-weighted super-sampling, extent
+                                       ceil(w f) x ceil(h f) -- instead of its OpenCV branch (cv::resize INTER_LINEAR, RetinaFace.cpp:613) */
 #define RF_FLAG_LEGACY_TC     0x10u /* FP16: one round-1 tensor-core kernel per layer (pair) instead of the persistent tile chains
                                        (tile_chain.cuh); the cross-check of the chains */
 
@@ -123,7 +126,9 @@ int rf_detect_batch(rf_handle h, const uint8_t *const *bgr_images, const int *wi
  * rf_collect_batch blocks until that batch's faces are in the caller's arrays.  Up to
  * RF_PIPELINE_DEPTH batches may be in flight, so the H2D copy of batch i+1 overlaps the kernels of
  * batch i (host ingest).  Tickets must be collected in submission order.  Source
- * images may be pinned (copied in place) or pageable (staged through the library's pinned ring). */
+ * images may be pinned (copied in place) or pageable (staged through the library's pinned ring).
+ * Every bgr_images[i] MUST point at net_h * net_w * 3 readable bytes (a packed network-sized image): there are no
+ * width / height / stride arguments here -- other sizes go through rf_detect_batch. */
 #define RF_PIPELINE_DEPTH 6
 int rf_submit_batch(rf_handle h, const uint8_t *const *bgr_images, int n, float score_threshold, float nms_threshold,
                     int *ticket);

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 RF_PREC_FP32, RF_PREC_FP16, RF_PREC_INT8 = 0, 1, 2
-RF_FLAG_NO_GRAPH, RF_FLAG_NO_TENSORCORE, RF_FLAG_SIMT_STEM, RF_FLAG_DW_1D, RF_FLAG_LEGACY_TC = 0x1, 0x2, 0x4, 0x8, 0x10
+RF_FLAG_NO_GRAPH, RF_FLAG_NO_TENSORCORE, RF_FLAG_SIMT_STEM, RF_FLAG_DW_1D, RF_FLAG_LEGACY_TC, RF_FLAG_NPP_RESIZE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 FACE_FLOATS = 15
 PIPELINE_DEPTH = 6   # RF_PIPELINE_DEPTH
 

@@ -316,8 +316,11 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
         const size_t in_bytes = (size_t)Bm * Hn * Wn * 3;
         CK(cudaMalloc(&h->d_input, in_bytes));
         CK(cudaHostAlloc(&h->h_input, in_bytes, cudaHostAllocDefault));
-        h->raw_bytes = (size_t)h->cfg.max_image_w * h->cfg.max_image_h * 3;
-        CK(cudaMalloc(&h->d_raw, h->raw_bytes));
+        h->raw_bytes = ((size_t)h->cfg.max_image_w * h->cfg.max_image_h * 3 + 255) / 256 * 256;
+        // one raw buffer per batch element (capped at 2 GiB in total): the images of a call are uploaded back to back and
+        // letter-boxed by ONE launch
+        h->raw_slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)Bm, ((size_t)2 << 30) / h->raw_bytes));
+        CK(cudaMalloc(&h->d_raw, h->raw_bytes * h->raw_slots));
         CK(cudaHostAlloc(&h->h_raw, 2 * h->raw_bytes, cudaHostAllocDefault));
         for (auto &e : h->raw_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaHostAlloc(&h->h_dets, sizeof(rf_det) * (size_t)Bm * h->cfg.max_faces, cudaHostAllocDefault));
@@ -480,12 +483,13 @@ static int fetch_results(rf_handle h, int n, rf_face *out_faces, int *out_counts
 // two pinned buffers: a row-band parallel host copy (host_copy.h) into one buffer overlaps the DMA out of the other; the
 // only host wait is for the DMA that last read the buffer about to be overwritten.  In both cases the stream orders the
 // copy into d_raw behind the letter-box kernel that still reads the previous image.
-static void upload_raw(rf_handle h, const uint8_t *src, int width, int height, int row_stride) {
+static uint8_t *upload_raw(rf_handle h, const uint8_t *src, int width, int height, int row_stride, int raw_slot = 0) {
+    uint8_t *d_dst = h->d_raw + (size_t)raw_slot * h->raw_bytes;
     cudaPointerAttributes at{};
     const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
     if (pinned) {
-        CK(cudaMemcpy2DAsync(h->d_raw, (size_t)width * 3, src, (size_t)row_stride, (size_t)width * 3, (size_t)height, cudaMemcpyHostToDevice, h->stream));
-        return;
+        CK(cudaMemcpy2DAsync(d_dst, (size_t)width * 3, src, (size_t)row_stride, (size_t)width * 3, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+        return d_dst;
     }
     cudaGetLastError();
     if (!h->copy_pool) h->copy_pool.reset(new HostCopyPool((int)std::min(3u, std::max(1u, std::thread::hardware_concurrency()) - 1u)));
@@ -493,8 +497,9 @@ static void upload_raw(rf_handle h, const uint8_t *src, int width, int height, i
     uint8_t *buf = h->h_raw + (size_t)slot * h->raw_bytes;
     CK(cudaEventSynchronize(h->raw_ev[slot]));      // (returns at once for an event never recorded)
     h->copy_pool->copy_rows(buf, src, (size_t)width * 3, (size_t)row_stride, height);
-    CK(cudaMemcpyAsync(h->d_raw, buf, (size_t)width * height * 3, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_dst, buf, (size_t)width * height * 3, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->raw_ev[slot], h->stream));
+    return d_dst;
 }
 
 int rf_detect_batch(rf_handle h, const uint8_t *const *imgs, const int *widths, const int *heights, const int *row_strides,
@@ -521,6 +526,15 @@ int rf_detect_batch(rf_handle h, const uint8_t *const *imgs, const int *widths, 
             run_start = -1;
         };
         bool staging_dirty = false;
+        // other sizes: uploaded into per-image raw buffers, then ONE letter-box launch for all of them (RF_FLAG_NPP_RESIZE: the
+        // reference's NPP super-sampling definition instead of its OpenCV bilinear one)
+        const int area = (h->cfg.flags & RF_FLAG_NPP_RESIZE) ? 1 : 0;
+        std::vector<LbItem> lb;
+        auto flush_lb = [&]() {
+            if (lb.empty()) return;
+            CK(launch_letterbox_batch(lb.data(), (int)lb.size(), Wn, Hn, h->stream));
+            lb.clear();
+        };
         for (int i = 0; i < n; i++) {
             if (!imgs[i] || widths[i] <= 0 || heights[i] <= 0) { return fail(h, RF_ERR_INVALID_ARG, fmt("rf_detect_batch: image %d is empty", i)); }
             const int rs = row_strides && row_strides[i] ? row_strides[i] : widths[i] * 3;
@@ -545,11 +559,14 @@ int rf_detect_batch(rf_handle h, const uint8_t *const *imgs, const int *widths, 
                 if (widths[i] > h->cfg.max_image_w || heights[i] > h->cfg.max_image_h)
                     return fail(h, RF_ERR_CAPACITY, fmt("image %d is %dx%d, larger than max_image %dx%d", i, widths[i], heights[i],
                                                         h->cfg.max_image_w, h->cfg.max_image_h));
-                upload_raw(h, imgs[i], widths[i], heights[i], rs);
-                launch_letterbox(h->d_raw, widths[i], heights[i], h->d_input + (size_t)i * img_bytes, Wn, Hn, h->stream);
+                if ((int)lb.size() == h->raw_slots) flush_lb();
+                const uint8_t *d_src = upload_raw(h, imgs[i], widths[i], heights[i], rs, (int)lb.size());
+                lb.emplace_back();
+                letterbox_fill(lb.back(), d_src, widths[i], heights[i], h->d_input + (size_t)i * img_bytes, Wn, Hn, 0, area);
             }
         }
         flush();
+        flush_lb();
         set_params(h, thr, nms);
         forward_graph(h, n);
         fetch_results(h, n, out_faces, out_counts, out_idx, nullptr);
@@ -750,16 +767,19 @@ int rf_detect_views(rf_handle h, const uint8_t *bgr, int width, int height, int 
         CK(cudaSetDevice(h->device));
         switch_ctx(h, 0);
         ensure_merge_buffers(h);
-        upload_raw(h, bgr, width, height, rs);
+        const uint8_t *d_src = upload_raw(h, bgr, width, height, rs);
         ViewSet vs{};
         vs.nviews = nviews;
         vs.img_w_minus1 = (float)(width - 1);
+        const int area = (h->cfg.flags & RF_FLAG_NPP_RESIZE) ? 1 : 0;
+        std::vector<LbItem> lb(nviews);
         for (int v = 0; v < nviews; v++) {
             const int bw = std::max(1, (int)(Wn * views[v].shrink)), bh = std::max(1, (int)(Hn * views[v].shrink));
             vs.flip[v] = views[v].flip ? 1 : 0;
-            vs.scale[v] = launch_letterbox_view(h->d_raw, width, height, h->d_input + (size_t)v * img_bytes, Wn, Hn, bw, bh, vs.flip[v], h->stream);
+            vs.scale[v] = letterbox_fill(lb[v], d_src, width, height, h->d_input + (size_t)v * img_bytes, bw, bh, vs.flip[v], area);
             if (out_view_scales) out_view_scales[v] = vs.scale[v];
         }
+        CK(launch_letterbox_batch(lb.data(), nviews, Wn, Hn, h->stream));     // all views of the image: one launch
         set_params(h, thr, nms);
         forward_graph(h, nviews);
         launch_merge_views(h->pb, vs, h->pb_merge, h->stream);
@@ -785,8 +805,10 @@ int rf_preprocess(rf_handle h, const uint8_t *bgr, int width, int height, int ro
     try {
         CK(cudaSetDevice(h->device));
         switch_ctx(h, 0);
-        upload_raw(h, bgr, width, height, rs);
-        launch_letterbox(h->d_raw, width, height, h->d_input, Wn, Hn, h->stream);
+        const uint8_t *d_src = upload_raw(h, bgr, width, height, rs);
+        LbItem it;
+        letterbox_fill(it, d_src, width, height, h->d_input, Wn, Hn, 0, (h->cfg.flags & RF_FLAG_NPP_RESIZE) ? 1 : 0);
+        CK(launch_letterbox_batch(&it, 1, Wn, Hn, h->stream));
         CK(cudaMemcpyAsync(h->h_input, h->d_input, (size_t)Hn * Wn * 3, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         memcpy(out, h->h_input, (size_t)Hn * Wn * 3);

@@ -19,6 +19,7 @@
 #include "host_copy.h"
 #include "model.h"
 #include "postproc.cuh"
+#include "preprocess.cuh"
 
 using namespace rf;
 
@@ -127,6 +128,7 @@ struct rf_handle_s {
     uint8_t *d_raw = nullptr;         // one raw caller image (max_image) for the letterbox kernel
     uint8_t *h_raw = nullptr;         // pinned, TWO buffers of raw_bytes: staging of pageable caller images (upload_raw)
     size_t raw_bytes = 0;
+    int raw_slots = 1;                // raw device buffers (one per batch element, capped)
     cudaEvent_t raw_ev[2] = {nullptr, nullptr};   // H2D out of staging buffer i has completed
     unsigned raw_seq = 0;
     std::unique_ptr<HostCopyPool> copy_pool;      // row-band parallel host copy into the staging buffers (lazily created)

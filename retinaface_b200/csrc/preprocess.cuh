@@ -11,8 +11,10 @@
 // Resize definition: the reference's OpenCV branch, cv::resize(img, Size(), 1/scale, 1/scale)
 // with INTER_LINEAR on 8UC3 -- OpenCV's fixed-point bilinear (coefficients rounded to 11 bits,
 // horizontal pass in int, vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2 >> 2).
-// Restated so results are BIT-IDENTICAL to cv2.resize (tests/test_preprocess.py).  The NPP
-// branch's super-sampling is a closed-source NPP routine and is not reproduced.
+// Restated so results are BIT-IDENTICAL to cv2.resize (tests/test_preprocess.py).
+// RF_FLAG_NPP_RESIZE selects the reference's OTHER branch instead (USE_NPP: imageROIResize8U3C -> nppiResizeSqrPixel_8u_C3R with
+// NPPI_INTER_SUPER): coverage-weighted super-sampling with NPP's measured edge rule (preprocess.cu area_pixel; checked against
+// NPP itself on a GPU box, oracle/npp_oracle.cu).
 #pragma once
 #include "common.cuh"
 
@@ -30,5 +32,20 @@ float launch_letterbox_view(const uint8_t *src, int w, int h, uint8_t *dst, int 
 
 // Host helper: output size + scale the way RetinaFace::detect + cv::resize compute them.
 void letterbox_geometry(int w, int h, int net_w, int net_h, int *dw, int *dh, double *inv_scale);
+// ... and the way imageROIResize8U3C + NPP do (resizeconvertion.cu:296-310): extent ceil(w f) x ceil(h f)
+void letterbox_geometry_npp(int w, int h, int net_w, int net_h, int *dw, int *dh, double *inv_scale);
+
+// Batched letter-box: ONE launch for up to LB_MAX_IMAGES images per call chunk, each with its own source / destination buffer;
+// 4 pixels (three 32-bit stores) per thread.
+constexpr int LB_MAX_IMAGES = 64;
+struct LbItem {
+    const uint8_t *src; uint8_t *dst;
+    int sw, sh, dw, dh;
+    double scale;
+    int identity, flip, area;
+};
+// fills one item (geometry of either resize definition); returns the reference's map-back factor
+float letterbox_fill(LbItem &it, const uint8_t *src, int w, int h, uint8_t *dst, int box_w, int box_h, int flip, int area);
+cudaError_t launch_letterbox_batch(const LbItem *items, int n, int net_w, int net_h, cudaStream_t s);
 
 }  // namespace rf

@@ -274,3 +274,64 @@ def test_comm_allgather_fused_into_nms_two_handles(golden_image):
     finally:
         for e in engs:
             e.close()
+
+
+def test_letterbox_npp_super_sampling_semantics(golden_image):
+    """RF_FLAG_NPP_RESIZE: the reference's USE_NPP letter-box (resizeconvertion.cu:279-316) against NPP itself (oracle/npp_oracle.cu
+    calls nppiResizeSqrPixel_8u_C3R exactly as the reference does) on 8 shapes: same extent, every byte within 1 LSB, at most
+    0.5 % of the bytes off by that 1 LSB (NPP accumulates in single precision), byte-identical on the shapes with integral
+    coverage.  And what the choice of branch does to the detections of the golden photo (printed)."""
+    from oracle.npp import npp_letterbox
+    from retinaface_b200 import RF_PREC_FP16, Engine
+    from retinaface_b200.capi import RF_FLAG_NPP_RESIZE
+    rng = np.random.default_rng(5)
+    cases = [(golden_image, 448, 448), (golden_image, 320, 320), (golden_image[100:600, 200:900], 448, 448),
+             (rng.integers(0, 256, (181, 297, 3), dtype=np.uint8), 96, 160), (rng.integers(0, 256, (333, 1000, 3), dtype=np.uint8), 448, 448),
+             (np.tile(np.arange(200, dtype=np.uint8).repeat(2)[None, :, None], (200, 1, 3)), 96, 160), (rng.integers(0, 256, (80, 100, 3), dtype=np.uint8), 448, 448),
+             (rng.integers(0, 256, (449, 449, 3), dtype=np.uint8), 448, 448)]
+    exact = 0
+    for img, nh, nw in cases:
+        img = np.ascontiguousarray(img)
+        eng = Engine(caffemodel("mnet25"), nh, nw, precision=RF_PREC_FP16, max_batch=1, max_image=(max(img.shape[0], nh), max(img.shape[1], nw)), flags=RF_FLAG_NPP_RESIZE)
+        try:
+            mine = eng.preprocess(img)
+        finally:
+            eng.close()
+        ref = npp_letterbox(img, nh, nw)
+        diff = np.abs(mine.astype(int) - ref.astype(int))
+        frac = np.count_nonzero(diff) / diff.size
+        print(f"{img.shape[1]}x{img.shape[0]} -> {nw}x{nh}: max diff {diff.max()}, {np.count_nonzero(diff)} of {diff.size} bytes differ ({frac:.4%})")
+        assert diff.max() <= 1 and frac <= 5e-3, (img.shape, nh, nw, diff.max(), frac)
+        assert np.array_equal(mine.any(axis=2), ref.any(axis=2)) or frac < 5e-3
+        exact += int(diff.max() == 0)
+    assert exact >= 4
+    # detections of the photo under either branch
+    e_lin = Engine(caffemodel("mnet25"), 448, 448, precision=RF_PREC_FP16, max_batch=1, max_image=golden_image.shape[:2])
+    e_npp = Engine(caffemodel("mnet25"), 448, 448, precision=RF_PREC_FP16, max_batch=1, max_image=golden_image.shape[:2], flags=RF_FLAG_NPP_RESIZE)
+    try:
+        a = e_lin.detect_batch([golden_image], 0.9, 0.4)[0]
+        b = e_npp.detect_batch([golden_image], 0.9, 0.4)[0]
+        pairs, ua, ub = _match(a, b)
+        ds = max((abs(float(a[i, 0] - b[j, 0])) for i, j in pairs), default=0.0)
+        dp = max((float(np.abs(a[i, 1:5] - b[j, 1:5]).max()) for i, j in pairs), default=0.0)
+        print(f"golden photo, OpenCV-bilinear vs NPP-super-sampling letter-box: {len(a)} vs {len(b)} faces, {len(pairs)} matched, score diff <= {ds:.4f}, box diff <= {dp:.2f} px")
+        assert len(pairs) >= 4
+    finally:
+        e_lin.close()
+        e_npp.close()
+
+
+def test_arbitrary_size_batch_is_one_letterbox_launch(golden_image):
+    """rf_detect_batch on a batch of differently sized caller images (pinned or pageable): uploaded into per-image raw buffers and
+    letter-boxed by one launch -- results equal those of the same images letter-boxed one by one through rf_preprocess."""
+    from retinaface_b200 import RF_PREC_FP16, Engine
+    imgs = [golden_image, np.ascontiguousarray(golden_image[:600, :900]), np.ascontiguousarray(golden_image[100:, 300:]), np.ascontiguousarray(golden_image[::2, ::2])]
+    eng = Engine(caffemodel("mnet25"), 448, 448, precision=RF_PREC_FP16, max_batch=4, max_image=golden_image.shape[:2])
+    try:
+        together = eng.detect_batch(imgs, 0.9, 0.4)
+        for i, im in enumerate(imgs):
+            alone = eng.detect_batch([eng.preprocess(im)], 0.9, 0.4)[0]
+            assert together[i].shape == alone.shape and np.array_equal(together[i], alone), i
+        assert len(together[0]) >= 4
+    finally:
+        eng.close()
