@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RF_B200_ABI_VERSION 1
+#define RF_B200_ABI_VERSION 2     /* 2: rf_config gained prototxt_path / cache_path / network (appended) */
 
 typedef enum rf_status {
     RF_OK = 0,
@@ -75,7 +75,17 @@ typedef struct rf_config {
     unsigned flags;                /* RF_FLAG_* */
     int streams;                   /* execution contexts the asynchronous entry points rotate through so that
                                       consecutive batches overlap on the GPU; 0 -> 4, max 4.  The blocking
-                                      rf_detect_batch always uses context 0. */
+                                      rf_detect_batch always uses context 0.  1 selects the latency-oriented layer plan. */
+    const char *prototxt_path;     /* optional: the Caffe prototxt of the model (buildTrtContext's first argument, RetinaFace.cpp:276).
+                                      Parsed as protobuf text, checked to be the RetinaFace mnet25 graph, and its per-layer
+                                      parameters (kernel, stride, group, bias_term, BatchNorm eps, ReLU) drive the weight folding;
+                                      net_w / net_h == 0 take the input size from it (trtnetbase.cpp:163-187).  NULL: built-in graph. */
+    const char *cache_path;        /* optional: file caching the folded model (the reference's engine cache, trtnetbase.cpp:205-243,
+                                      which is never invalidated); reused only for the exact caffemodel (+ prototxt) bytes it was
+                                      made from, rewritten otherwise.  NULL: no cache. */
+    const char *network;           /* optional: the reference's network name (RetinaFace.cpp:205: "net3" default).  Names whose
+                                      configuration the reference itself cannot run (net5, net6 ...: :266-268) or that need more
+                                      anchors than the shipped models have (net3a) are refused with RF_ERR_UNSUPPORTED. */
 } rf_config;
 
 #define RF_FLAG_NO_GRAPH      0x1u  /* launch kernels directly instead of replaying a CUDA graph */
@@ -244,6 +254,16 @@ int rf_debug_keep_all(rf_handle h);
 /* Host-only (works without a GPU): the folded FP32 weights / bias of one convolution layer as the
  * engine holds them; dims = {cout, cin/groups, k, k}.  For CPU-side tests of the model front end. */
 int rf_model_inspect(const char *caffemodel_path, const char *layer, float *w, int wcap, float *b, int bcap, int dims[4]);
+/* Host-only model front end.  rf_model_load: the complete load path of rf_create -- cache lookup, prototxt parse +
+ * graph check, file-driven folding, cache write -- without a device; *cache_status: 0 no cache, 1 miss (written), 2 hit,
+ * 3 stale (rewritten); input_dims: N, C, H, W of the prototxt (zeros without one); then rf_model_inspect semantics for `layer`
+ * (may be NULL).  rf_network_config: the reference's network-name switch (RetinaFace.cpp:211-268): FPN strides, anchor scales per
+ * level (2 each), ratios; RF_ERR_UNSUPPORTED where the reference prints "please reconfig anchor_cfg". */
+int rf_model_load(const char *caffemodel_path, const char *prototxt_path, const char *cache_path, int *cache_status, int input_dims[4],
+                  const char *layer, float *w, int wcap, float *b, int bcap, int dims[4]);
+int rf_network_config(const char *network, int *num_levels, int strides[3], int scales[6], float ratios[2], int *num_ratios);
+/* Cache state of a handle's model load (the enum above). */
+int rf_cache_status(rf_handle h);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,7 @@ SOURCES = [
     ("preprocess.cu", ["-fmad=false"]),
     ("calibrate.cu", []),
     ("model.cpp", []),
+    ("frontend.cpp", []),
 ]
 
 

@@ -24,6 +24,7 @@ EXPORTS = [
     "rf_detect_views", "rf_plan_describe",
     "rf_comm_export", "rf_comm_init", "rf_comm_nccl_unique_id", "rf_comm_init_nccl", "rf_comm_info", "rf_detect_batch_device_allgather",
     "rf_submit_batch_allgather", "rf_collect_batch_allgather", "rf_detect_batch_allgather",
+    "rf_model_load", "rf_network_config", "rf_cache_status",
 ]
 COMM_BLOB_BYTES = 128
 
@@ -42,7 +43,7 @@ class _Config(C.Structure):
     _fields_ = [("caffemodel_path", C.c_char_p), ("int8_table_path", C.c_char_p), ("precision", C.c_int),
                 ("net_w", C.c_int), ("net_h", C.c_int), ("max_batch", C.c_int), ("max_faces", C.c_int),
                 ("device", C.c_int), ("max_image_w", C.c_int), ("max_image_h", C.c_int), ("flags", C.c_uint),
-                ("streams", C.c_int)]
+                ("streams", C.c_int), ("prototxt_path", C.c_char_p), ("cache_path", C.c_char_p), ("network", C.c_char_p)]
 
 
 def lib_path() -> str:
@@ -99,6 +100,7 @@ def load_library() -> C.CDLL:
     lib.rf_calibrate_int8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p]
     lib.rf_kl_threshold_bins.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.rf_kl_threshold_bins.restype = C.c_double
+    lib.rf_cache_status.argtypes = [C.c_void_p]
     lib.rf_comm_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.rf_comm_init.argtypes = [C.c_void_p, C.c_void_p]
     lib.rf_comm_nccl_unique_id.argtypes = [C.c_void_p]
@@ -133,13 +135,48 @@ def plan_describe(caffemodel: str, net_h: int, net_w: int, precision: int = RF_P
                   int8_table: Optional[str] = None, streams: int = 0) -> str:
     """The layer plan rf_create would build (host-only entry point: no GPU needed)."""
     lib = load_library()
-    cfg = _Config(caffemodel.encode(), int8_table.encode() if int8_table else None, precision, net_w, net_h, max_batch, 0, 0, 0, 0, flags, streams)
+    cfg = _Config(caffemodel.encode(), int8_table.encode() if int8_table else None, precision, net_w, net_h, max_batch, 0, 0, 0, 0, flags, streams, None, None, None)
     buf = C.create_string_buffer(1 << 16)
     lib.rf_plan_describe.argtypes = [C.POINTER(_Config), C.c_char_p, C.c_int]
     rc = lib.rf_plan_describe(C.byref(cfg), buf, len(buf))
     if rc < 0:
         raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
     return buf.value.decode()
+
+
+def model_load(caffemodel: str, prototxt: Optional[str] = None, cache: Optional[str] = None, layer: Optional[str] = None):
+    """rf_model_load (host-only): the load path of rf_create.  Returns (cache_status, input_dims, (w, b) of `layer` or None)."""
+    lib = load_library()
+    lib.rf_model_load.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                  C.POINTER(C.c_int)]
+    cs = C.c_int(0)
+    idims = (C.c_int * 4)()
+    dims = (C.c_int * 4)()
+    args = (caffemodel.encode(), prototxt.encode() if prototxt else None, cache.encode() if cache else None, C.byref(cs), idims, layer.encode() if layer else None)
+    rc = lib.rf_model_load(*args, None, 0, None, 0, dims)
+    if rc != 0:
+        raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
+    wb = None
+    if layer:
+        w = np.empty(tuple(dims), dtype=np.float32)
+        b = np.empty(dims[0], dtype=np.float32)
+        rc = lib.rf_model_load(*args, w.ctypes.data_as(C.c_void_p), w.size, b.ctypes.data_as(C.c_void_p), b.size, dims)
+        if rc != 0:
+            raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
+        wb = (w, b)
+    return cs.value, tuple(idims), wb
+
+
+def network_config(network: str):
+    """rf_network_config: (strides, scales per level, ratios) of the reference's network-name switch; RfError(-7) where unsupported."""
+    lib = load_library()
+    lib.rf_network_config.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    nl, nr = C.c_int(0), C.c_int(0)
+    strides, scales, ratios = (C.c_int * 3)(), (C.c_int * 6)(), (C.c_float * 2)()
+    rc = lib.rf_network_config(network.encode(), C.byref(nl), strides, scales, ratios, C.byref(nr))
+    if rc != 0:
+        raise RfError(rc, (lib.rf_last_error(None) or b"").decode())
+    return list(strides)[:nl.value], [list(scales)[2 * i:2 * i + 2] for i in range(nl.value)], list(ratios)[:nr.value]
 
 
 def nccl_unique_id() -> bytes:
@@ -171,15 +208,21 @@ class Engine:
 
     def __init__(self, caffemodel: str, net_h: int, net_w: int, precision: int = RF_PREC_FP16, max_batch: int = 8,
                  max_faces: int = 256, device: int = 0, int8_table: Optional[str] = None,
-                 max_image: Optional[Tuple[int, int]] = None, flags: int = 0, streams: int = 0):
+                 max_image: Optional[Tuple[int, int]] = None, flags: int = 0, streams: int = 0, prototxt: Optional[str] = None,
+                 cache: Optional[str] = None, network: Optional[str] = None):
         self.lib = load_library()
         cfg = _Config(caffemodel.encode(), int8_table.encode() if int8_table else None, precision, net_w, net_h,
-                      max_batch, max_faces, device, max_image[1] if max_image else 0, max_image[0] if max_image else 0, flags, streams)
+                      max_batch, max_faces, device, max_image[1] if max_image else 0, max_image[0] if max_image else 0, flags, streams,
+                      prototxt.encode() if prototxt else None, cache.encode() if cache else None, network.encode() if network else None)
         h = C.c_void_p()
         rc = self.lib.rf_create(C.byref(cfg), C.byref(h))
         if rc != 0:
             raise RfError(rc, (self.lib.rf_last_error(None) or b"").decode())
         self.h = h
+        if net_h == 0 and net_w == 0:          # taken from the prototxt
+            nw, nh = C.c_int(), C.c_int()
+            self.lib.rf_get_net_size(h, C.byref(nw), C.byref(nh), None, None)
+            net_h, net_w = nh.value, nw.value
         self.net_h, self.net_w = net_h, net_w
         self.max_batch, self.precision, self.device = max_batch, precision, device
         mf = C.c_int()

@@ -222,6 +222,24 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
     if (out) *out = nullptr;
     if (!cfg || !out) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_create: cfg and out must be non-NULL");
     if (!cfg->caffemodel_path) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_create: caffemodel_path is NULL");
+    rf_config cfg_local = *cfg;
+    NetGraph graph;
+    Model model;
+    int cache_status = CACHE_NONE;
+    {
+        // model front end first: the prototxt may supply the network size (trtnetbase.cpp:163-187 reads it from there too)
+        std::string err;
+        int st = RF_OK;
+        if (cfg->network) {
+            NetworkConfig nc;
+            if (!network_config(cfg->network, nc, err)) return fail(nullptr, RF_ERR_UNSUPPORTED, "rf_create: " + err);
+            if (nc.ratios.size() != 1) return fail(nullptr, RF_ERR_UNSUPPORTED, fmt("rf_create: network '%s' uses %zu anchor ratios per scale; the shipped models (and this engine) have 2 anchors per position", cfg->network, nc.ratios.size()));
+        }
+        if (!load_model(cfg->caffemodel_path, cfg->prototxt_path ? cfg->prototxt_path : "", cfg->cache_path ? cfg->cache_path : "", model, &graph, &cache_status, err, st))
+            return fail(nullptr, st, err);
+        if (cfg->prototxt_path && cfg_local.net_w == 0 && cfg_local.net_h == 0) { cfg_local.net_h = graph.input_dims[2]; cfg_local.net_w = graph.input_dims[3]; }
+    }
+    cfg = &cfg_local;
     if (cfg->net_w <= 0 || cfg->net_h <= 0 || cfg->net_w % 32 || cfg->net_h % 32)
         return fail(nullptr, RF_ERR_INVALID_ARG, fmt("rf_create: net size %dx%d must be positive multiples of 32", cfg->net_w, cfg->net_h));
     if (cfg->max_batch <= 0 || cfg->max_batch > 4096) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_create: max_batch must be in [1, 4096]");
@@ -256,11 +274,10 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
 
     // ---- model (host) --------------------------------------------------------------------
     {
-        std::vector<RawLayer> layers;
         std::string err;
-        bool io = false;
-        if (!read_caffemodel(h->caffemodel, layers, err, io)) return fail(nullptr, io ? RF_ERR_IO : RF_ERR_MODEL, err);
-        if (!build_mnet_model(layers, h->model, err)) return fail(nullptr, RF_ERR_MODEL, err);
+        h->model = std::move(model);
+        h->cache_status = cache_status;
+        h->cfg.prototxt_path = h->cfg.cache_path = h->cfg.network = nullptr;     // (the caller's strings are not kept)
         if (!h->table.empty() && !read_int8_table(h->table, h->int8_scales, err)) return fail(nullptr, RF_ERR_IO, err);
     }
     // ---- device ----------------------------------------------------------------------------
@@ -994,6 +1011,44 @@ double rf_kl_threshold_bins(const unsigned *hist, int bins, int levels) { return
 // Host-only (no GPU needed): folded FP32 weights/bias of one convolution as the engine will hold
 // them (BatchNorm + Scale + bias folded).  dims = {cout, cin/groups, k, k}.  Lets CPU-only tests
 // check the model front end against the oracle's fold.
+int rf_cache_status(rf_handle h) { return h ? h->cache_status : RF_ERR_INVALID_ARG; }
+
+int rf_network_config(const char *network, int *num_levels, int strides[3], int scales[6], float ratios[2], int *num_ratios) {
+    if (!network) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_network_config: NULL network");
+    NetworkConfig nc;
+    std::string err;
+    const bool ok = network_config(network, nc, err);
+    if (num_ratios) *num_ratios = (int)nc.ratios.size();
+    if (ratios) for (size_t i = 0; i < nc.ratios.size() && i < 2; i++) ratios[i] = nc.ratios[i];
+    if (!ok) return fail(nullptr, RF_ERR_UNSUPPORTED, err);
+    if (num_levels) *num_levels = (int)nc.strides.size();
+    for (size_t l = 0; l < nc.strides.size() && l < 3; l++) {
+        if (strides) strides[l] = nc.strides[l];
+        if (scales) { scales[2 * l] = nc.scales[l][0]; scales[2 * l + 1] = nc.scales[l][1]; }
+    }
+    return RF_OK;
+}
+
+int rf_model_load(const char *caffemodel_path, const char *prototxt_path, const char *cache_path, int *cache_status, int input_dims[4],
+                  const char *layer, float *w, int wcap, float *b, int bcap, int dims[4]) {
+    if (!caffemodel_path) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_model_load: NULL caffemodel_path");
+    Model m;
+    NetGraph g;
+    std::string err;
+    int st = RF_OK, cs = CACHE_NONE;
+    if (!load_model(caffemodel_path, prototxt_path ? prototxt_path : "", cache_path ? cache_path : "", m, &g, &cs, err, st)) return fail(nullptr, st, err);
+    if (cache_status) *cache_status = cs;
+    if (input_dims) for (int k = 0; k < 4; k++) input_dims[k] = g.input_dims[k];
+    if (!layer) return RF_OK;
+    auto it = m.convs.find(layer);
+    if (it == m.convs.end()) return fail(nullptr, RF_ERR_INVALID_ARG, std::string("no convolution '") + layer + "'");
+    const FoldedConv &c = it->second;
+    if (dims) { dims[0] = c.cout; dims[1] = c.cin / c.groups; dims[2] = c.k; dims[3] = c.k; }
+    if (w) { if ((size_t)wcap < c.w.size()) return fail(nullptr, RF_ERR_CAPACITY, "w buffer too small"); memcpy(w, c.w.data(), c.w.size() * 4); }
+    if (b) { if ((size_t)bcap < c.b.size()) return fail(nullptr, RF_ERR_CAPACITY, "b buffer too small"); memcpy(b, c.b.data(), c.b.size() * 4); }
+    return RF_OK;
+}
+
 int rf_model_inspect(const char *caffemodel_path, const char *layer, float *w, int wcap, float *b, int bcap, int dims[4]) {
     if (!caffemodel_path || !layer) return fail(nullptr, RF_ERR_INVALID_ARG, "rf_model_inspect: NULL argument");
     std::vector<RawLayer> layers;

@@ -105,6 +105,7 @@ struct rf_handle_s {
     std::vector<std::shared_ptr<TileChain>> chains;   // tile-chain launches of the FP16 plan (plan_tile.cu)
     unsigned tile_mask = 0;                           // which parts of the FP16 plan run as tile chains (RF_TILE_MASK)
     int lane_last[3] = {-1, -1, -1};                  // last step of each side lane (joined at the end of the forward)
+    int cache_status = 0;                             // model.h CACHE_*: how the folded model was obtained
     bool profiling = false;                           // rf_profile_layers is launching single steps out of their forward
     int tile_expected = 0;                            // tiles per image over the three SSH chains (last-block NMS)
     std::vector<float> tile_bias_tmp;                 // plan-time scratch

@@ -104,7 +104,7 @@ bool read_caffemodel(const std::string &path, std::vector<RawLayer> &layers, std
 
 namespace {
 
-struct Spec { std::string name, bn; int cin, cout, k, stride, groups; bool bias, relu; double eps; };
+struct Spec { std::string name, bn; int cin, cout, k, stride, groups; bool bias, relu; double eps; std::string scale; };
 
 void head_conv(std::vector<Spec> &v, const std::string &name, int cin, int cout, int k, bool relu) {
     v.push_back({name, name + "_bn", cin, cout, k, 1, 1, true, relu, 2e-5});
@@ -153,9 +153,11 @@ std::vector<Spec> mnet_specs() {
 
 }  // namespace
 
-bool build_mnet_model(const std::vector<RawLayer> &layers, Model &m, std::string &err) {
+bool build_mnet_model(const std::vector<RawLayer> &layers, Model &m, std::string &err, const std::vector<ConvSpec> *graph_specs) {
     std::map<std::string, const RawLayer *> by_name;
     for (auto &L : layers) by_name[L.name] = &L;
+    std::map<std::string, const ConvSpec *> from_file;
+    if (graph_specs) for (auto &g : *graph_specs) from_file[g.name] = &g;
     auto need = [&](const std::string &n, const char *type, size_t nblobs) -> const RawLayer * {
         auto it = by_name.find(n);
         if (it == by_name.end()) { err = "caffemodel lacks layer '" + n + "' (not an mnet25 RetinaFace model)"; return nullptr; }
@@ -163,7 +165,22 @@ bool build_mnet_model(const std::vector<RawLayer> &layers, Model &m, std::string
         if (it->second->blobs.size() < nblobs) { err = "layer '" + n + "' holds " + std::to_string(it->second->blobs.size()) + " blobs, expected " + std::to_string(nblobs); return nullptr; }
         return it->second;
     };
-    for (const Spec &s : mnet_specs()) {
+    for (Spec s : mnet_specs()) {
+        if (graph_specs) {
+            // the prototxt's own description of this layer drives the folding; it must be the layer the plan expects
+            auto it = from_file.find(s.name);
+            if (it == from_file.end()) { err = "prototxt lacks convolution '" + s.name + "'"; return false; }
+            const ConvSpec &g = *it->second;
+            if (g.cout != s.cout || g.k != s.k || g.stride != s.stride || g.groups != s.groups || g.relu != s.relu || g.bn.empty() != s.bn.empty() || g.pad != (s.k == 3 ? 1 : 0)) {
+                err = "prototxt: convolution '" + s.name + "' is " + std::to_string(g.cout) + " outputs, k" + std::to_string(g.k) + " s" + std::to_string(g.stride) + " g" +
+                      std::to_string(g.groups) + " pad" + std::to_string(g.pad) + (g.relu ? " +ReLU" : "") + (g.bn.empty() ? "" : " +BN") + "; the engine's plan expects " + std::to_string(s.cout) +
+                      " outputs, k" + std::to_string(s.k) + " s" + std::to_string(s.stride) + " g" + std::to_string(s.groups) + (s.relu ? " +ReLU" : "") + (s.bn.empty() ? "" : " +BN");
+                return false;
+            }
+            s.bias = g.bias;
+            s.eps = g.eps;
+            if (!g.bn.empty()) { s.bn = g.bn; s.scale = g.scale; }
+        }
         const RawLayer *L = need(s.name, "Convolution", s.bias ? 2 : 1);
         if (!L) return false;
         size_t wn = (size_t)s.cout * (s.cin / s.groups) * s.k * s.k;
@@ -179,7 +196,7 @@ bool build_mnet_model(const std::vector<RawLayer> &layers, Model &m, std::string
         if (!s.bn.empty()) {
             const RawLayer *B = need(s.bn, "BatchNorm", 3);
             if (!B) return false;
-            const RawLayer *S = need(s.bn + "_scale", "Scale", 2);
+            const RawLayer *S = need(s.scale.empty() ? s.bn + "_scale" : s.scale, "Scale", 2);
             if (!S) return false;
             for (int i = 0; i < 2; i++)
                 if (B->blobs[i].data.size() != (size_t)s.cout || S->blobs[i].data.size() != (size_t)s.cout) {
@@ -209,6 +226,32 @@ bool build_mnet_model(const std::vector<RawLayer> &layers, Model &m, std::string
         if (L->blobs[0].data.size() != 64 * 16) { err = std::string("layer '") + ups[i] + "': expected 64x1x4x4 weights"; return false; }
         m.up_w[i] = L->blobs[0].data;
     }
+    return true;
+}
+
+bool load_model(const std::string &caffemodel, const std::string &prototxt, const std::string &cache_path, Model &m, NetGraph *graph,
+                int *cache_status, std::string &err, int &status) {
+    // rf_status values (include/rf_b200.h): IO -2, MODEL -3
+    if (cache_status) *cache_status = CACHE_NONE;
+    NetGraph g;
+    std::vector<ConvSpec> specs;
+    bool io = false;
+    if (!prototxt.empty()) {
+        if (!read_prototxt(prototxt, g, err, io)) { status = io ? -2 : -3; return false; }
+        if (!check_mnet_topology(g, err) || !graph_conv_specs(g, specs, err)) { status = -3; return false; }
+        if (graph) *graph = g;
+    }
+    ModelCacheKey key;
+    if (!cache_path.empty()) {
+        if (!model_cache_key(caffemodel, prototxt, key)) { err = "cannot open caffemodel '" + caffemodel + "'"; status = -2; return false; }
+        const int st = load_model_cache(cache_path, key, m);
+        if (cache_status) *cache_status = st;
+        if (st == CACHE_HIT) return true;
+    }
+    std::vector<RawLayer> layers;
+    if (!read_caffemodel(caffemodel, layers, err, io)) { status = io ? -2 : -3; return false; }
+    if (!build_mnet_model(layers, m, err, prototxt.empty() ? nullptr : &specs)) { status = -3; return false; }
+    if (!cache_path.empty() && !save_model_cache(cache_path, key, m)) { err = "cannot write the model cache '" + cache_path + "'"; status = -2; return false; }
     return true;
 }
 

@@ -7,11 +7,18 @@
 
 RetinaFace::RetinaFace(string &model, string network_, float nms, const RetinaFaceOptions &opt)
     : opt_(opt), network(network_), nms_threshold(nms) {
-    // RetinaFace.cpp:211-271: only the fmc == 3 "net3" anchor configuration is ever set up
-    if (network != "net3") throw std::runtime_error("network setting error " + network + ": only net3 is configured");
+    // RetinaFace.cpp:211-271: the network-name switch lives behind the C ABI (rf_network_config / rf_config.network); names the
+    // reference itself has no anchor configuration for (fmc != 3) or whose models do not ship (net3a) are refused there
+    int levels = 0, nratios = 0;
+    if (rf_network_config(network.c_str(), &levels, nullptr, nullptr, nullptr, &nratios) != RF_OK)
+        throw std::runtime_error("network setting error " + network + ": " + rf_last_error(nullptr));
     const string path = model + "/" + opt_.model_file;
     rf_config cfg{};
     const string table = model + "/" + opt_.int8_table_file;
+    const string proto = opt_.prototxt_file.empty() ? string() : model + "/" + opt_.prototxt_file;
+    cfg.network = network.c_str();
+    cfg.prototxt_path = proto.empty() ? nullptr : proto.c_str();     // buildTrtContext(prototxt, caffemodel), RetinaFace.cpp:276
+    cfg.cache_path = opt_.cache_file.empty() ? nullptr : opt_.cache_file.c_str();
     cfg.caffemodel_path = path.c_str();
     cfg.int8_table_path = opt_.precision == RF_PREC_INT8 ? table.c_str() : nullptr;
     cfg.precision = opt_.precision;
@@ -24,7 +31,7 @@ RetinaFace::RetinaFace(string &model, string network_, float nms, const RetinaFa
     cfg.max_image_h = opt_.max_image_h;
     int rc = rf_create(&cfg, &h_);
     if (rc != RF_OK) throw std::runtime_error(string("rf_create: ") + rf_status_string(rc) + ": " + rf_last_error(nullptr));
-    rf_get_net_size(h_, nullptr, nullptr, nullptr, &opt_.max_faces);
+    rf_get_net_size(h_, &opt_.net_w, &opt_.net_h, nullptr, &opt_.max_faces);     // (0 x 0: the prototxt's input size)
     out_faces_.resize((size_t)opt_.max_batch * opt_.max_faces);
     out_counts_.resize(opt_.max_batch);
 }

@@ -36,6 +36,10 @@ struct RetinaFaceOptions {
     int max_image_w = 4096, max_image_h = 3072;   // RetinaFace.cpp:325
     string model_file = "mnet-deconv-0517.caffemodel";   // RetinaFace.cpp:276
     string int8_table_file = "mnet-deconv-0517.table.int8";   // used when precision == RF_PREC_INT8 (trtnetbase.cpp:13)
+    string prototxt_file;                // e.g. "mnet-deconv-0517.prototxt" (RetinaFace.cpp:276): parsed, checked, drives the weight
+                                         // folding; with net_w = net_h = 0 it also sets the network size.  Empty: built-in graph
+    string cache_file;                   // folded-model cache (the reference's "retina.cache", trtnetbase.cpp:205-243, but with a
+                                         // staleness check).  Empty: none
 };
 
 class RetinaFace {

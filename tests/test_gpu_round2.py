@@ -335,3 +335,26 @@ def test_arbitrary_size_batch_is_one_letterbox_launch(golden_image):
         assert len(together[0]) >= 4
     finally:
         eng.close()
+
+
+def test_engine_from_prototxt_with_cache(golden_image, tmp_path):
+    """rf_create through the model front end: the prototxt supplies the network size (the reference reads it from prototxt line 7), the
+    folded model is cached (miss, then hit) and the detections equal those of the built-in graph at the same size."""
+    from retinaface_b200 import RF_PREC_FP16, Engine
+    proto = tmp_path / "net.prototxt"
+    proto.write_text(topology.to_prototxt(416, 288, 1))          # mnet25.prototxt's own size (H 416, W 288)
+    cache = str(tmp_path / "net.rfcache")
+    img = letterbox_bgr_u8(golden_image, 416, 288)
+    ref = _engine("mnet25", 416, 288, RF_PREC_FP16, max_batch=1)
+    want = ref.detect_batch([img], 0.5, 0.4)[0]
+    ref.close()
+    for expect in (1, 2):
+        eng = Engine(caffemodel("mnet25"), 0, 0, precision=RF_PREC_FP16, max_batch=1, prototxt=str(proto), cache=cache, network="net3")
+        try:
+            assert (eng.net_h, eng.net_w) == (416, 288)
+            assert eng.lib.rf_cache_status(eng.h) == expect
+            got = eng.detect_batch([img], 0.5, 0.4)[0]
+            assert got.shape == want.shape and np.array_equal(got, want)
+        finally:
+            eng.close()
+    assert len(want) >= 1

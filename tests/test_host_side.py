@@ -18,7 +18,7 @@ def test_exports_every_declared_symbol(built_lib):
     lib = C.CDLL(built_lib)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rf_abi_version() == 1
+    assert lib.rf_abi_version() == 2
 
 
 def test_product_has_no_oracle_dependency():
