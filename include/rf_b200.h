@@ -74,7 +74,7 @@ typedef struct rf_config {
     int max_image_w, max_image_h;  /* largest caller image (reference: 4096x3072, RetinaFace.cpp:325); 0 -> net size */
     unsigned flags;                /* RF_FLAG_* */
     int streams;                   /* execution contexts the asynchronous entry points rotate through so that
-                                      consecutive batches overlap on the GPU; 0 -> 4, max 4.  The blocking
+                                      consecutive batches overlap on the GPU; 0 -> 6, max RF_MAX_STREAMS.  The blocking
                                       rf_detect_batch always uses context 0.  1 selects the latency-oriented layer plan. */
     const char *prototxt_path;     /* optional: the Caffe prototxt of the model (buildTrtContext's first argument, RetinaFace.cpp:276).
                                       Parsed as protobuf text, checked to be the RetinaFace mnet25 graph, and its per-layer
@@ -139,6 +139,7 @@ int rf_detect_batch(rf_handle h, const uint8_t *const *bgr_images, const int *wi
  * images may be pinned (copied in place) or pageable (staged through the library's pinned ring).
  * Every bgr_images[i] MUST point at net_h * net_w * 3 readable bytes (a packed network-sized image): there are no
  * width / height / stride arguments here -- other sizes go through rf_detect_batch. */
+#define RF_MAX_STREAMS 8
 #define RF_PIPELINE_DEPTH 6
 int rf_submit_batch(rf_handle h, const uint8_t *const *bgr_images, int n, float score_threshold, float nms_threshold,
                     int *ticket);

@@ -19,13 +19,14 @@ def main():
     ap.add_argument("--warm", type=int, default=3)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--streams", type=int, default=0, help="execution contexts (1 = the latency plan: tile chains)")
     args = ap.parse_args()
     wl = bench.WORKLOADS[args.workload]
     from retinaface_b200 import RF_PREC_FP16, RF_PREC_FP32, Engine
     from retinaface_b200.capi import RF_FLAG_NO_GRAPH
     eng = Engine(os.path.join(bench.GOLD, "weights", wl["model"] + ".caffemodel"), wl["h"], wl["w"],
                  precision=RF_PREC_FP16 if wl["precision"] == "fp16" else RF_PREC_FP32, max_batch=wl["batch"], max_faces=128,
-                 flags=RF_FLAG_NO_GRAPH if args.no_graph else 0)
+                 flags=RF_FLAG_NO_GRAPH if args.no_graph else 0, streams=args.streams)
     batch = bench.make_batches(wl, 1, 0)[0]
     eng.pinned_input()[:] = batch
     print("launches per step:", eng.launches_per_batch(wl["batch"]))

@@ -280,6 +280,83 @@ __global__ void __launch_bounds__(128) k_mma_rate(int n, int count, int nacc, in
     if (warp == 1) tc::tmem_dealloc<512>(tmem);
 }
 
+// MMA throughput with NOTHING but the instructions in the issuing thread: fully unrolled, every operand a compile-time offset
+// from one base.  LAYOUT 0: SW128 A (64-channel rows, K-step = 32 B of each 128-byte row); 1: no-swizzle planes (16 B per
+// row per K-chunk).  D rotates over NACC accumulators, A over 9 row shifts x 4 K-steps like a depthwise / 3x3 issue block.
+template <int N, int NACC, int TS, int LAYOUT>
+__global__ void __launch_bounds__(128) k_mma_rate2(long long *out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 96 * 1024 / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { tc::mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 1) tc::tmem_alloc<512>(&s_tmem);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    constexpr int COUNT = 144;
+    if (warp == 0) {
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        if (leader) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t a_addr = tc::smem_u32(smem), b_addr = a_addr + 64 * 1024;
+            const uint64_t a0 = LAYOUT == 0 ? sw_desc(a_addr, 1024, 2, 0) : tc::smem_desc(a_addr, 24 * 1024, 128);
+            const uint64_t b0 = tc::smem_desc(b_addr, (uint32_t)N * 16, 128);
+            const long long t0 = clock64();
+#pragma unroll
+            for (int i = 0; i < COUNT; i++) {
+                const int t = (i / 4) % 9, k = i % 4;
+                const uint64_t ad = a0 + (uint64_t)(LAYOUT == 0 ? ((t * 7 + 3) * 128 + k * 32) / 16 : ((t * 7 + 3) * 16 + (k & 1) * 8 * 1024) / 16);
+                const uint64_t bd = b0 + (uint64_t)((i % 8) * 512 / 16);
+                const uint32_t d = tmem + (uint32_t)((i % NACC) * N);
+                if (TS) {
+                    if (i >= NACC)
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                                     ::"r"(d), "r"(tmem + 448u), "l"(bd), "r"(idesc) : "memory");
+                    else
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                                     ::"r"(d), "r"(tmem + 448u), "l"(bd), "r"(idesc) : "memory");
+                } else {
+                    if (i >= NACC)
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+                    else
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(d), "l"(ad), "l"(bd), "r"(idesc) : "memory");
+                }
+            }
+            const long long t1 = clock64();
+            tc::mma_commit(&bar);
+            tc::mbar_wait(&bar, 0);
+            const long long t2 = clock64();
+            out[0] = t1 - t0; out[1] = t2 - t0;
+        }
+        __syncwarp();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+template <int N, int NACC, int TS, int LAYOUT>
+static void run_rate2(long long *dout) {
+    CKC(cudaFuncSetAttribute(k_mma_rate2<N, NACC, TS, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    long long best[2] = {1ll << 60, 1ll << 60};
+    for (int rep = 0; rep < 3; rep++) {
+        k_mma_rate2<N, NACC, TS, LAYOUT><<<1, 128, 100 * 1024>>>(dout);
+        CKC(cudaDeviceSynchronize());
+        long long h2[2];
+        CKC(cudaMemcpy(h2, dout, 16, cudaMemcpyDeviceToHost));
+        if (h2[1] < best[1]) { best[0] = h2[0]; best[1] = h2[1]; }
+    }
+    printf("rate2 %s %s N=%3d accumulators=%d: issue %5.1f cyc/MMA, complete %6.1f cyc/MMA (144 MMAs, M=128 K=16)\n", TS ? "TS" : "SS",
+           LAYOUT ? "noswz" : "sw128", N, NACC, best[0] / 144.0, best[1] / 144.0);
+}
+
 struct StoreMaps { CUtensorMap in; CUtensorMap st[3]; };
 // loads a box with maps.in and stores it back through maps.st[idx] at (0, sx, sy, b)
 __global__ void __launch_bounds__(128) k_store_probe(const __grid_constant__ StoreMaps maps, int idx, int lx, int ly, int sx, int sy, int b, unsigned bytes) {
@@ -444,6 +521,16 @@ int main(int argc, char **argv) {
         }
         printf("s2: elementStrides {1,2,2,1}, hypothesis box(lx,ly) <- (x0+2lx, y0+2ly): mismatches %ld of %d\n", bad, 64 * C);
         return bad ? 1 : 0;
+    }
+    if (test == "rate2") {
+        long long *dout;
+        CKC(cudaMalloc(&dout, 16));
+        run_rate2<16, 1, 0, 0>(dout); run_rate2<16, 4, 0, 0>(dout); run_rate2<16, 4, 0, 1>(dout); run_rate2<32, 4, 0, 0>(dout);
+        run_rate2<48, 2, 0, 0>(dout); run_rate2<64, 1, 0, 0>(dout); run_rate2<64, 2, 0, 0>(dout); run_rate2<64, 2, 0, 1>(dout);
+        run_rate2<128, 1, 0, 0>(dout); run_rate2<128, 2, 0, 0>(dout); run_rate2<256, 1, 0, 0>(dout);
+        run_rate2<16, 4, 1, 0>(dout); run_rate2<32, 2, 1, 0>(dout); run_rate2<64, 1, 1, 0>(dout); run_rate2<64, 2, 1, 0>(dout);
+        run_rate2<128, 2, 1, 0>(dout); run_rate2<256, 1, 1, 0>(dout);
+        return 0;
     }
     if (test == "rate") {
         long long *dout;
