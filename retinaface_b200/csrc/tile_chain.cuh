@@ -26,8 +26,11 @@
 // Epilogue threads write stage outputs into shared memory in the same swizzled layout (thread = position).
 //
 // Depthwise on tensor cores.  out[p][c] = sum_t in[p + shift_t][c] * w_t[c] is 9 * C/16 MMAs with M = 128, N = K = 16 and
-// B = diag(w_t[16 channels]) accumulating into TMEM columns [16 s, 16 s + 16): 8 tensor cycles each, instead of ~130
-// CUDA-core instructions per 8 channels.  The mid-epilogue (TMEM -> + bias, ReLU, FP16) writes the result back to TMEM
+// B = diag(w_t[16 channels]) accumulating into TMEM columns [16 s, 16 s + 16): no CUDA-core instruction per tap, but each
+// such MMA occupies the tensor pipe for 37.7 cycles, not the 8 its math needs -- an SS-mode MMA re-reads its 4 KB A operand
+// from shared memory whatever N is (tools/umma_probe.cu rate2: SS 37.7 / 46 / 61 cycles at N = 16 / 64 / 128, TS N/2), so a
+// 64-channel depthwise stage is tensor-pipe bound at 36 x 37.7 = 1357 cycles per 128 positions (the chains' traces agree:
+// DESIGN.md section 3).  The mid-epilogue (TMEM -> + bias, ReLU, FP16) writes the result back to TMEM
 // in place as packed FP16 and the pointwise GEMM takes its A operand from TMEM (.kind::f16 with [a_tmem]).
 //
 // Roles (320 threads): warp 0 = TMA producer (tiles, per-stage weights, TMA stores), warp 1 = MMA issuer (one elected
