@@ -1,5 +1,6 @@
 // common.cuh -- shared device/host helpers of librf_b200 (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -59,6 +60,11 @@ template <> __device__ __forceinline__ __half from_f<__half>(float x) { return _
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// RF_NO_PDL=1 (read once): launch without the attribute -- griddepcontrol.* are then no-ops (A/B measurements)
+inline bool pdl_allowed() {
+    static const bool on = [] { const char *e = getenv("RF_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg{};
@@ -66,7 +72,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_allowed() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 

@@ -96,6 +96,8 @@ void place_tensors(rf_handle h, bool keep_all) {
 // Issue the forward pass: lane 0 on `s`, side lanes on their own streams, joined by events.  Works both
 // under stream capture (the side streams fork from / join into the capturing stream) and eagerly.
 void run_steps(rf_handle h, int n, cudaStream_t s, bool use_lanes = true) {
+    static const bool one_lane = [] { const char *e = getenv("RF_ONE_LANE"); return e && e[0] == '1'; }();   // A/B measurements
+    if (one_lane) use_lanes = false;
     for (size_t i = 0; i < h->steps.size(); i++) {
         Step &st = h->steps[i];
         cudaStream_t cs = (use_lanes && st.lane) ? h->lane_stream[st.lane] : s;

@@ -702,7 +702,10 @@ static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
 }
 
 void build_plan_tiles(rf_handle h) {
-    const unsigned mask = (unsigned)env_int("RF_TILE_MASK", (int)(h->cfg.streams == 1 ? TM_LATENCY : TM_THROUGHPUT));
+    // the chain plan pays off for one forward at a time AND small batches (profiles/r02_mask_sweep.txt: batch 1 / 8, one
+    // context: 118.8 / 178.6 us against 124.5 / 184.1 us; batch 32: 456 against 420 us -- there every kernel fills the GPU)
+    const bool latency_mode = h->cfg.streams == 1 && h->cfg.max_batch <= 16;
+    const unsigned mask = (unsigned)env_int("RF_TILE_MASK", (int)(latency_mode ? TM_LATENCY : TM_THROUGHPUT));
     for (unsigned m : {mask, mask & ~(unsigned)(TM_HEAD | TM_NMS)}) {
         // a failed attempt leaves no trace
         h->steps.clear(); h->tensors.clear(); h->tensor_by_name.clear(); h->chains.clear();
