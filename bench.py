@@ -384,11 +384,13 @@ def main():
             barrier()
             return (time.perf_counter() - t0) * 1e3
 
+        lat = [None]
+
         def blk_block():
             barrier()
             t0 = time.perf_counter()
             for _ in range(K):
-                eng.detect_batch([pin_np[pos[0] % ring, j] for j in range(B)], SCORE_THR, NMS_THR)
+                lat[0].detect_batch([pin_np[pos[0] % ring, j] for j in range(B)], SCORE_THR, NMS_THR)
                 pos[0] += 1
             barrier()
             return (time.perf_counter() - t0) * 1e3
@@ -423,9 +425,14 @@ def main():
                           timing=f"host wall clock, median over blocks of K rf_submit_batch{'_allgather' if gather else ''}/rf_collect steps, {depth} batches in flight"
                                  + ("; every step's results are the records of ALL ranks, host-visible" if gather else ""))
         if full and not gather:
+            # latency mode is its own handle configuration: streams = 1 selects the chain plan
+            lat[0] = Engine(os.path.join(GOLD, "weights", w["model"] + ".caffemodel"), H, Wd, precision=prec, max_batch=B, max_faces=128, device=local,
+                            streams=1, int8_table=os.path.join(GOLD, "weights", w["model"] + ".table.int8") if prec == RF_PREC_INT8 else None)
             b_ms, b_n, b_s = run_blocks(blk_block, 1)
             out["e2e"]["blocking"] = dict(value=faces_step * K / (b_ms * 1e-3), ms_per_step=b_ms / K, images_per_s=K * B * world / (b_ms * 1e-3),
-                                          note="one blocking rf_detect_batch per step (latency mode)")
+                                          launches_per_step=lat[0].launches_per_batch(B),
+                                          note="one blocking rf_detect_batch per step on a streams=1 handle (latency mode: chain plan)")
+            lat[0].close()
         if clock is not None:
             out["clocks"] = clock.summary()
         if full and rank == 0:
