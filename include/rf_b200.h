@@ -155,6 +155,20 @@ int rf_collect_batch(rf_handle h, int ticket, rf_face *out_faces, int *out_count
 int rf_detect_batch_device(rf_handle h, const uint8_t *dev_bgr, int n, float score_threshold,
                            float nms_threshold, const rf_det **dev_dets, const int32_t **dev_counts);
 
+/* f1 ingest, compressed: the reference decodes its test images on the host (cv::imread, main.cpp:18-26) and then copies
+ * pixels; here the JPEG bitstreams are decoded ON the GPU (nvJPEG, opened at run time; hardware JPEG engines when the device
+ * and the stream allow it, nvJPEG's hybrid back end otherwise) into the same device buffers the pixel path letter-boxes from,
+ * so a camera-sized photo crosses PCIe as its compressed bytes.  jpegs[i] / jpeg_bytes[i]: host memory.  Images may have any
+ * size up to max_image; out_widths / out_heights (optional) receive the decoded sizes (map-back: RetinaFace.cpp:732-738).
+ * Results as rf_detect_batch.  RF_ERR_UNSUPPORTED when libnvjpeg is absent. */
+int rf_detect_jpeg_batch(rf_handle h, const uint8_t *const *jpegs, const size_t *jpeg_bytes, int n, float score_threshold,
+                         float nms_threshold, rf_face *out_faces, int *out_counts, int32_t *out_anchor_index, int *out_widths,
+                         int *out_heights);
+/* Decode only (parity / callers that want the pixels): BGR u8, packed rows, into out_bgr (host, out_capacity bytes);
+ * out_bgr == NULL just reports the size.  rf_jpeg_backend: "hardware" | "default" | "none" (+ what the last call used). */
+int rf_decode_jpeg(rf_handle h, const uint8_t *jpeg, size_t bytes, uint8_t *out_bgr, size_t out_capacity, int *width, int *height);
+const char *rf_jpeg_backend(rf_handle h);
+
 /* ---- Multi-GPU (the reference is single-GPU: `ctx_id`, RetinaFace.h:89, is never used) --------------------
  * One process (handle) per GPU; the batch is sharded over the ranks, weights are replicated, and the ONLY exchange is an
  * all-gather of the per-image detection records -- fused into the NMS kernel: the CTA that finishes an image stores its kept

@@ -21,6 +21,7 @@ SOURCES = [
     ("plan_i8.cu", []),
     ("plan_tile.cu", []),
     ("comm.cu", []),
+    ("jpeg.cu", []),
     ("postproc.cu", ["-fmad=false"]),
     ("preprocess.cu", ["-fmad=false"]),
     ("calibrate.cu", []),

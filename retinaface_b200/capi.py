@@ -25,6 +25,7 @@ EXPORTS = [
     "rf_comm_export", "rf_comm_init", "rf_comm_nccl_unique_id", "rf_comm_init_nccl", "rf_comm_info", "rf_detect_batch_device_allgather",
     "rf_submit_batch_allgather", "rf_collect_batch_allgather", "rf_detect_batch_allgather",
     "rf_model_load", "rf_network_config", "rf_cache_status",
+    "rf_detect_jpeg_batch", "rf_decode_jpeg", "rf_jpeg_backend",
 ]
 COMM_BLOB_BYTES = 128
 
@@ -110,6 +111,11 @@ def load_library() -> C.CDLL:
     lib.rf_submit_batch_allgather.argtypes = lib.rf_submit_batch.argtypes
     lib.rf_collect_batch_allgather.argtypes = lib.rf_collect_batch.argtypes
     lib.rf_detect_batch_allgather.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rf_detect_jpeg_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+    lib.rf_decode_jpeg.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.rf_jpeg_backend.restype = C.c_char_p
+    lib.rf_jpeg_backend.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
@@ -292,6 +298,31 @@ class Engine:
         if want_index:
             return out, [idx[i, :counts[i]].copy() for i in range(n)]
         return out
+
+    def detect_jpeg(self, streams: Sequence[bytes], thr: float, nms_thr: float):
+        """JPEG bitstreams (bytes) -> decoded on the GPU (nvJPEG), letter-boxed, detected.  Returns (list of (k,15) arrays in
+        network-input pixels, list of (width, height) of the decoded images)."""
+        n = len(streams)
+        bufs = [np.frombuffer(b, dtype=np.uint8) for b in streams]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_size_t * n)(*[b.size for b in bufs])
+        faces = np.empty((n, self.max_faces, FACE_FLOATS), dtype=np.float32)
+        counts = np.zeros(n, dtype=np.int32)
+        ws, hs = (C.c_int * n)(), (C.c_int * n)()
+        self._check(self.lib.rf_detect_jpeg_batch(self.h, ptrs, lens, n, thr, nms_thr, faces.ctypes.data, counts.ctypes.data, None, ws, hs))
+        return [faces[i, :counts[i]].copy() for i in range(n)], [(ws[i], hs[i]) for i in range(n)]
+
+    def decode_jpeg(self, stream: bytes) -> np.ndarray:
+        """nvJPEG decode of one stream -> (h, w, 3) u8 BGR (what rf_detect_jpeg_batch letter-boxes)."""
+        buf = np.frombuffer(stream, dtype=np.uint8)
+        w, hh = C.c_int(), C.c_int()
+        self._check(self.lib.rf_decode_jpeg(self.h, buf.ctypes.data, buf.size, None, 0, C.byref(w), C.byref(hh)))
+        out = np.empty((hh.value, w.value, 3), dtype=np.uint8)
+        self._check(self.lib.rf_decode_jpeg(self.h, buf.ctypes.data, buf.size, out.ctypes.data, out.nbytes, C.byref(w), C.byref(hh)))
+        return out
+
+    def jpeg_backend(self) -> str:
+        return self.lib.rf_jpeg_backend(self.h).decode()
 
     def detect_pinned(self, n: int, thr: float, nms_thr: float, faces: np.ndarray, counts: np.ndarray):
         """Hot-loop variant for bench.py: the n images are already in pinned_input(); results go

@@ -153,6 +153,7 @@ void destroy(rf_handle h) {
     if (h->saved.empty()) h->saved.resize(1);
     for (int c = 0; c < (int)h->saved.size(); c++) { switch_ctx(h, c); if (h->stream) cudaStreamSynchronize(h->stream); }
     comm_release(h);
+    jpeg_release(h);
     for (int c = 0; c < (int)h->saved.size(); c++) {
         switch_ctx(h, c);
         if (h->stream) cudaStreamSynchronize(h->stream);
@@ -592,6 +593,78 @@ int rf_detect_batch(rf_handle h, const uint8_t *const *imgs, const int *widths, 
     } catch (const CudaFail &f) { return fail_cuda(h, f); }
     return RF_OK;
 }
+
+// ---- f1 ingest: compressed images (main.cpp:18-26 decodes on the host with cv::imread) ---------------------------------------
+int rf_detect_jpeg_batch(rf_handle h, const uint8_t *const *jpegs, const size_t *jpeg_bytes, int n, float thr, float nms, rf_face *out_faces,
+                         int *out_counts, int32_t *out_idx, int *out_widths, int *out_heights) {
+    int rc = check_n(h, n);
+    if (rc) return rc;
+    if (n == 0) return RF_OK;
+    if (!jpegs || !jpeg_bytes) return fail(h, RF_ERR_INVALID_ARG, "rf_detect_jpeg_batch: NULL stream arrays");
+    const int Hn = h->cfg.net_h, Wn = h->cfg.net_w;
+    const size_t img_bytes = (size_t)Hn * Wn * 3;
+    try {
+        CK(cudaSetDevice(h->device));
+        switch_ctx(h, 0);
+        std::vector<int> w(n), hg(n);
+        for (int i = 0; i < n; i++) {
+            if (!jpegs[i] || !jpeg_bytes[i]) return fail(h, RF_ERR_INVALID_ARG, fmt("rf_detect_jpeg_batch: stream %d is empty", i));
+            if ((rc = jpeg_info(h, jpegs[i], jpeg_bytes[i], &w[i], &hg[i]))) return rc;
+            if (w[i] <= 0 || hg[i] <= 0 || w[i] > h->cfg.max_image_w || hg[i] > h->cfg.max_image_h)
+                return fail(h, RF_ERR_CAPACITY, fmt("JPEG %d is %dx%d, larger than max_image %dx%d", i, w[i], hg[i], h->cfg.max_image_w, h->cfg.max_image_h));
+            if (out_widths) out_widths[i] = w[i];
+            if (out_heights) out_heights[i] = hg[i];
+        }
+        const int area = (h->cfg.flags & RF_FLAG_NPP_RESIZE) ? 1 : 0;
+        // network-sized images decode straight into the input tensor; the others into the raw buffers, a chunk of raw_slots at
+        // a time, each chunk letter-boxed by one launch (all of it stream-ordered: a raw buffer is reused only behind its reader)
+        for (int i0 = 0; i0 < n;) {
+            std::vector<uint8_t *> dst;
+            std::vector<LbItem> lb;
+            int i1 = i0, used = 0;
+            for (; i1 < n; i1++) {
+                const bool direct = w[i1] == Wn && hg[i1] == Hn;
+                if (!direct && used == h->raw_slots) break;
+                dst.push_back(direct ? h->d_input + (size_t)i1 * img_bytes : h->d_raw + (size_t)used * h->raw_bytes);
+                if (!direct) {
+                    lb.emplace_back();
+                    letterbox_fill(lb.back(), dst.back(), w[i1], hg[i1], h->d_input + (size_t)i1 * img_bytes, Wn, Hn, 0, area);
+                    used++;
+                }
+            }
+            if ((rc = jpeg_decode(h, jpegs + i0, jpeg_bytes + i0, i1 - i0, dst.data(), w.data() + i0, hg.data() + i0, h->stream))) return rc;
+            if (!lb.empty()) CK(launch_letterbox_batch(lb.data(), (int)lb.size(), Wn, Hn, h->stream));
+            i0 = i1;
+        }
+        set_params(h, thr, nms);
+        forward_graph(h, n);
+        fetch_results(h, n, out_faces, out_counts, out_idx, nullptr);
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+int rf_decode_jpeg(rf_handle h, const uint8_t *jpeg, size_t bytes, uint8_t *out_bgr, size_t out_capacity, int *width, int *height) {
+    if (!h) return RF_ERR_INVALID_ARG;
+    if (!jpeg || !bytes || !width || !height) return fail(h, RF_ERR_INVALID_ARG, "rf_decode_jpeg: NULL argument");
+    try {
+        CK(cudaSetDevice(h->device));
+        switch_ctx(h, 0);
+        int rc = jpeg_info(h, jpeg, bytes, width, height);
+        if (rc) return rc;
+        if (!out_bgr) return RF_OK;                                    // size query
+        const size_t need = (size_t)*width * *height * 3;
+        if (need > out_capacity) return fail(h, RF_ERR_CAPACITY, fmt("rf_decode_jpeg: %dx%d needs %zu bytes, the buffer has %zu", *width, *height, need, out_capacity));
+        if (*width > h->cfg.max_image_w || *height > h->cfg.max_image_h)
+            return fail(h, RF_ERR_CAPACITY, fmt("JPEG is %dx%d, larger than max_image %dx%d", *width, *height, h->cfg.max_image_w, h->cfg.max_image_h));
+        uint8_t *dst = h->d_raw;
+        if ((rc = jpeg_decode(h, &jpeg, &bytes, 1, &dst, width, height, h->stream))) return rc;
+        CK(cudaMemcpyAsync(out_bgr, h->d_raw, need, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    } catch (const CudaFail &f) { return fail_cuda(h, f); }
+    return RF_OK;
+}
+
+const char *rf_jpeg_backend(rf_handle h) { return h ? jpeg_backend(h) : "none"; }
 
 static void ensure_slots(rf_handle h) {
     if (h->copy_stream) return;

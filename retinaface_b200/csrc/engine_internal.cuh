@@ -184,6 +184,7 @@ struct rf_handle_s {
     unsigned next_dev_ctx = 0;
     cudaStream_t last_stream = nullptr;
     cudaEvent_t fence = nullptr;
+    void *jpeg = nullptr;             // nvJPEG decoder state (jpeg.cu), created by the first JPEG call
 };
 
 namespace rf_eng {
@@ -277,6 +278,11 @@ std::string describe_chains(rf_handle h);
 // ---- exported by comm.cu --------------------------------------------------------------------------------------------
 void comm_release(rf_handle h);
 void comm_wait(rf_handle h, unsigned seq, unsigned slot, int n, cudaStream_t s);
+// ---- exported by jpeg.cu (f1 ingest: nvJPEG decode into device memory) ------------------------------------------------
+int jpeg_info(rf_handle h, const uint8_t *data, size_t len, int *w, int *hgt);
+int jpeg_decode(rf_handle h, const uint8_t *const *data, const size_t *len, int n, uint8_t *const *dst, const int *w, const int *hgt, cudaStream_t s);
+void jpeg_release(rf_handle h);
+const char *jpeg_backend(rf_handle h);
 // ---- exported by plan_i8.cu -----------------------------------------------------------------------------------------
 void build_plan_i8(rf_handle h);
 cudaError_t tc_init_i8();

@@ -405,3 +405,51 @@ def test_calibrator_under_the_references_conditions(golden_image, tmp_path):
         assert missing == 0, (len(faces), len(gold))
     finally:
         eng.close()
+
+
+def test_jpeg_ingest_decodes_on_the_gpu(golden_image):
+    """rf_detect_jpeg_batch (f1 ingest, compressed half; main.cpp:18-26 decodes with cv::imread on the host): JPEG bitstreams ->
+    nvJPEG decode in device memory -> batched letter-box -> detect.  Checked against the host path on cv2.imdecode pixels of the
+    same streams: the decoders (libjpeg-turbo vs nvJPEG) are allowed their IDCT / chroma-upsampling differences -- decoded bytes
+    within a small mean error -- and the detections must be the same faces."""
+    import cv2
+    from retinaface_b200 import RF_PREC_FP16, Engine
+    from retinaface_b200.capi import RfError
+    raw = open(os.path.join(GOLDEN, "data", "img.jpg"), "rb").read()
+    streams = [raw]
+    for im, q, extra in [(golden_image[:, ::-1], 92, []), (golden_image[::2, ::2], 85, []), (golden_image[100:548, 300:748], 95, []),
+                         (golden_image, 90, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])]:
+        ok, enc = cv2.imencode(".jpg", np.ascontiguousarray(im), [cv2.IMWRITE_JPEG_QUALITY, q] + extra)
+        assert ok
+        streams.append(enc.tobytes())
+    eng = Engine(caffemodel("mnet25"), 448, 448, precision=RF_PREC_FP16, max_batch=8, max_image=golden_image.shape[:2])
+    try:
+        try:
+            faces, sizes = eng.detect_jpeg(streams, 0.9, 0.4)
+        except RfError as e:
+            if e.status == -7 or "libnvjpeg" in str(e):
+                pytest.skip("libnvjpeg not present on this box")
+            raise
+        print("nvJPEG back end:", eng.jpeg_backend())
+        host_imgs = [cv2.imdecode(np.frombuffer(s, np.uint8), cv2.IMREAD_COLOR) for s in streams]
+        ref = eng.detect_batch(host_imgs, 0.9, 0.4)
+        for i, (s, im) in enumerate(zip(streams, host_imgs)):
+            assert sizes[i] == (im.shape[1], im.shape[0]), (i, sizes[i], im.shape)
+            dec = eng.decode_jpeg(s)
+            assert dec.shape == im.shape
+            d = np.abs(dec.astype(np.int32) - im.astype(np.int32))
+            print(f"stream {i} ({im.shape[1]}x{im.shape[0]}, {len(s)} bytes): decoded bytes vs cv2.imdecode mean |diff| {d.mean():.3f}, max {d.max()}, "
+                  f"faces {len(faces[i])} vs {len(ref[i])}")
+            assert d.mean() < 1.5, (i, d.mean())
+            pairs, extra_mine, missed = _match(faces[i], ref[i])
+            assert extra_mine == 0 and missed == 0, (i, len(faces[i]), len(ref[i]))
+            for a, b in pairs:
+                assert abs(faces[i][a][0] - ref[i][b][0]) < 0.03 and np.abs(faces[i][a][1:] - ref[i][b][1:]).max() < 2.0
+        assert len(faces[0]) >= 4
+        # a stream that is not a JPEG is an error, not a crash
+        with pytest.raises(RfError):
+            eng.detect_jpeg([b"not a jpeg at all" * 10], 0.9, 0.4)
+        # and the pixel path still works afterwards
+        assert len(eng.detect_batch([host_imgs[0]], 0.9, 0.4)[0]) == len(ref[0])
+    finally:
+        eng.close()
