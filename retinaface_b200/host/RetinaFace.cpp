@@ -47,6 +47,29 @@ void RetinaFace::detect(const Mat &img, float threshold, float /*scales*/) {
     detectBatchImages(one, threshold);
 }
 
+void RetinaFace::detectEncoded(const vector<vector<unsigned char>> &jpegs, float threshold) {
+    last_.assign(jpegs.size(), vector<FaceDetectInfo>());
+    scales_.assign(jpegs.size(), 1.f);
+    const size_t mb = (size_t)opt_.max_batch;
+    for (size_t start = 0; start < jpegs.size(); start += mb) {
+        const int n = (int)std::min(mb, jpegs.size() - start);
+        vector<const uint8_t *> ptrs(n);
+        vector<size_t> lens(n);
+        vector<int> ws(n), hs(n);
+        for (int i = 0; i < n; i++) { ptrs[i] = jpegs[start + i].data(); lens[i] = jpegs[start + i].size(); }
+        int rc = rf_detect_jpeg_batch(h_, ptrs.data(), lens.data(), n, threshold, nms_threshold, out_faces_.data(), out_counts_.data(), nullptr,
+                                      ws.data(), hs.data());
+        if (rc != RF_OK) throw std::runtime_error(string("rf_detect_jpeg_batch: ") + rf_status_string(rc) + ": " + rf_last_error(h_));
+        for (int i = 0; i < n; i++) {
+            float sw = 1.0f * ws[i] / opt_.net_w, sh = 1.0f * hs[i] / opt_.net_h;   // RetinaFace.cpp:587-591
+            float sc = sw > sh ? sw : sh;
+            scales_[start + i] = sc > 1.0f ? sc : 1.0f;
+            const FaceDetectInfo *f = reinterpret_cast<const FaceDetectInfo *>(out_faces_.data() + (size_t)i * opt_.max_faces);
+            last_[start + i].assign(f, f + out_counts_[i]);
+        }
+    }
+}
+
 void RetinaFace::detectBatchImages(vector<cv::Mat> imgs, float threshold) {
     last_.assign(imgs.size(), vector<FaceDetectInfo>());
     scales_.assign(imgs.size(), 1.f);

@@ -51,6 +51,9 @@ class RetinaFace {
 
     void detectBatchImages(vector<cv::Mat> imgs, float threshold = 0.5);
     void detect(const Mat &img, float threshold = 0.5, float scales = 1.0);
+    // compressed input: what main.cpp:18-26 hands to cv::imread.  The JPEG bitstreams are decoded on the GPU
+    // (rf_detect_jpeg_batch); results and lastScale() as for detectBatchImages
+    void detectEncoded(const vector<vector<unsigned char>> &jpegs, float threshold = 0.5);
 
     // results of the last call, in network-input pixels (RetinaFace.cpp:707); multiply by
     // lastScale() to map back to the caller's image (RetinaFace.cpp:587-591, 732-738)

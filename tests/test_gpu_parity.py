@@ -355,6 +355,13 @@ def test_cpp_driver_on_golden_photo(golden_image, tmp_path):
     red = (out == (0, 0, 255)).all(axis=2) & changed
     green = (out == (0, 255, 0)).all(axis=2) & changed
     assert red.sum() > 5 * 400 and green.sum() >= 5 * 5 * 6 and (changed == (red | green)).all()
+    # the reference's own input form (main.cpp:18: a JPEG file): decoded on the GPU
+    r = subprocess.run([exe, os.path.join(GOLDEN, "weights"), "--jpeg", os.path.join(GOLDEN, "data", "img.jpg"), "--net", "448", "448", "--iters", "3",
+                        "--batch", "2"], capture_output=True, text=True, timeout=120)
+    if "libnvjpeg" in r.stderr:
+        pytest.skip("libnvjpeg not present on this box")
+    assert r.returncode == 0, r.stderr
+    assert "5 faces in image 0" in r.stdout and "score 0.9" in r.stdout and "JPEG decoded on the GPU" in r.stdout
 
 
 def test_pipelined_submit_collect_equals_blocking(golden_image):
