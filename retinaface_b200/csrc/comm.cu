@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(1024) k_comm_wait(const unsigned *flags, size_
     for (int t = threadIdx.x; t < world * n; t += blockDim.x) {
         const int r = t / n, i = t - r * n;
         const volatile unsigned *f = flags + base + (size_t)r * max_batch + i;
-        unsigned v, spins = 0;
-        while ((v = *f) != seq) {
+        unsigned spins = 0;
+        while (*f != seq) {
             if (++spins > (1u << 25)) { atomicMax(err, 1u + (unsigned)r); break; }   // a peer never delivered: report, do not hang
             __nanosleep(200);
         }
