@@ -1,5 +1,6 @@
 // common.cuh -- shared device/host helpers of librf_b200 (sm_100a only).
 #pragma once
+#include <cstdint>
 #include <cstdlib>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -50,6 +51,11 @@ __device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
 template <typename T> __device__ __forceinline__ T from_f(float x);
 template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
 template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
+
+// ---- division by a launch constant: q = umulhi(n, ceil(2^32 / d)), exact while n * d < 2^32 (n, d >= 1; d == 1: mul = 0 marks
+// the identity).  An integer division by a run-time value costs ~25 instructions; the 2-D depthwise kernels did five per thread.
+inline uint32_t fast_div_mul(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); }
+__device__ __forceinline__ int fast_div(int n, uint32_t mul) { return mul ? (int)__umulhi((uint32_t)n, mul) : n; }
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------
 // Every kernel of the forward pass is launched with cudaLaunchAttributeProgrammaticStreamSerialization:

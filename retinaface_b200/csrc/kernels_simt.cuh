@@ -434,13 +434,14 @@ namespace rf {
 static __global__ void __launch_bounds__(256) k_fpn_merge_h2(const __half *__restrict__ lateral, const __half *__restrict__ up,
                                                       __half *__restrict__ out, const __half *__restrict__ uwh, int n, int H, int W, int C) {
     pdl_trigger();
-    const int cg = C >> 3, UH = H >> 1, UW = W >> 1;
-    const long total = (long)n * H * W * cg;
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int g = (int)(idx % cg);
-    const long pix = idx / cg;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+    // grid = (row pieces, H, images): no division (the 64-bit ones of the first version were most of this kernel's instructions);
+    // C / 8 is a power of two (host-checked)
+    const int cg = C >> 3, lg = 31 - __clz(cg), UH = H >> 1, UW = W >> 1;
+    const int t_row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_row >= W * cg) return;
+    const int g = t_row & (cg - 1), x = t_row >> lg, y = blockIdx.y, b = blockIdx.z;
+    const long pix = ((long)b * H + y) * W + x;
+    (void)n;
     const int c0 = g * 8;
     const int i_hi = (y + 1) >> 1, j_hi = (x + 1) >> 1;
     int ci[2], cj[2], ky[2], kx[2];
@@ -480,13 +481,12 @@ namespace rf {
 static __global__ void __launch_bounds__(256) k_fpn_merge_i8(const int8_t *__restrict__ lateral, const int8_t *__restrict__ up, int8_t *__restrict__ out,
                                                       const float *__restrict__ wq, float lat_mul, int n, int H, int W, int C) {
     pdl_trigger();
-    const int cg = C >> 4, UH = H >> 1, UW = W >> 1;
-    const long total = (long)n * H * W * cg;
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int g = (int)(idx % cg);
-    const long pix = idx / cg;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+    const int cg = C >> 4, lg = 31 - __clz(cg), UH = H >> 1, UW = W >> 1;     // grid = (row pieces, H, images); C / 16 a power of two
+    const int t_row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_row >= W * cg) return;
+    const int g = t_row & (cg - 1), x = t_row >> lg, y = blockIdx.y, b = blockIdx.z;
+    const long pix = ((long)b * H + y) * W + x;
+    (void)n;
     const int c0 = g * 16;
     const int i_hi = (y + 1) >> 1, j_hi = (x + 1) >> 1;
     pdl_wait();

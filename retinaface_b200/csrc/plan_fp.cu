@@ -288,8 +288,8 @@ int plan_fpn_merge_h2(Builder &B, const std::string &name, int tlat, int tup, in
     s.flops_per_img = 2.0 * fh * fw * 64 * 4;
     s.bytes_per_img = ((double)fh * fw * 64 * 2 + (double)(fh / 2) * (fw / 2) * 64) * es;
     s.launch = [=](int n, cudaStream_t st) {
-        long total = (long)n * fh * fw * 8;
-        CK(launch_k(k_fpn_merge_h2, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const __half *)T_(tlat), (const __half *)T_(tup),
+        // 128 threads per block: a 56-pixel row is 448 (pixel, 8-channel) items = 3.5 blocks
+        CK(launch_k(k_fpn_merge_h2, dim3((unsigned)((fw * 8 + 127) / 128), (unsigned)fh, (unsigned)n), dim3(128), 0, st, (const __half *)T_(tlat), (const __half *)T_(tup),
                     (__half *)T_(plus), (const __half *)(h->d_weights_h + ouw), n, fh, fw, 64));
     };
     B.step(std::move(s));

@@ -321,8 +321,7 @@ void build_plan_i8(rf_handle h) {
         s.flops_per_img = 2.0 * h8 * w8 * 64 * 4;
         s.bytes_per_img = (double)h8 * w8 * 64 * 2 + (double)(h8 / 2) * (w8 / 2) * 64;
         s.launch = [=](int n, cudaStream_t st) {
-            long total = (long)n * h8 * w8 * 4;
-            launch_k(k_fpn_merge_i8, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const int8_t *)Q_(lat1), (const int8_t *)Q_(aggr2), Q_(plus1),
+            launch_k(k_fpn_merge_i8, dim3((unsigned)((w8 * 4 + 127) / 128), (unsigned)h8, (unsigned)n), dim3(128), 0, st, (const int8_t *)Q_(lat1), (const int8_t *)Q_(aggr2), Q_(plus1),
                      Wd(owq), lat_mul, n, h8, w8, 64);
         };
         B.step(std::move(s));

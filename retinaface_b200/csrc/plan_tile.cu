@@ -510,7 +510,7 @@ static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
 
     // a backbone chain over pairs `is` (first may be stride 2) + optionally one trailing 1x1 conv on the last pair's output;
     // falls back to round-1 kernels pair by pair
-    int c1 = -1, c2 = -1, c3 = -1, lat1 = -1, lat2 = -1, lat3 = -1;
+    int lat1 = -1, lat2 = -1, lat3 = -1;
     auto backbone = [&](const std::string &name, std::vector<int> is, bool enabled, const char *lat_conv, int *lat_out, int lane_lat) {
         const int S = pair(is[0]).first->stride;
         const int oh = cur_h / S, ow = cur_w / S;
@@ -569,7 +569,6 @@ static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
         backbone("A", {3, 5}, mask & TM_A, nullptr, nullptr, 0);
         backbone("B", {7, 9}, mask & TM_B, "rf_c1_red_conv", &lat1, 1);
     }
-    c1 = cur;
     const int h8 = cur_h, w8 = cur_w;
     if (single) {
         backbone("C11", {11}, mask & TM_C, nullptr, nullptr, 0);
@@ -582,13 +581,10 @@ static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
         backbone("C", {11, 13, 15}, mask & TM_C, nullptr, nullptr, 0);
         backbone("D", {17, 19, 21}, mask & TM_D, "rf_c2_lateral", &lat2, 2);
     }
-    c2 = cur;
     const int h16 = cur_h, w16 = cur_w;
     backbone("E", {23}, mask & TM_E, nullptr, nullptr, 0);
     backbone("F", {25}, false, "rf_c3_lateral", &lat3, 0);
-    c3 = cur;
     const int h32 = cur_h, w32 = cur_w;
-    (void)c1; (void)c2; (void)c3;
 
     // ---- FPN top-down + SSH ---------------------------------------------------------------------------------------------
     // levels: 0 = stride 32 (lat3, no merge), 1 = stride 16, 2 = stride 8

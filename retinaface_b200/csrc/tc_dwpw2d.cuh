@@ -22,6 +22,7 @@ struct TcDw2dArgs {
     int tiles_x, tiles_y;
     int PH, PW;             // staged window: (TH-1)*S+3 x (TW-1)*S+3   (tc_dw2d_finish)
     uint32_t lbo_a;         // group stride of the A operand, bytes (tc_dw2d_finish)
+    uint32_t mul_TW, mul_tiles_x, mul_tiles;   // fast_div multipliers (tc_dw2d_finish)
     const __half *wimg;     // [C/8][N][8]
     const float *bias;      // [N]
     const float *dw_w, *dw_b;   // [9][C], [C]
@@ -40,6 +41,9 @@ inline void tc_dw2d_finish(TcDw2dArgs &a) {
     a.tiles_x = (a.OW + a.TW - 1) / a.TW;
     a.tiles_y = (a.OH + a.TH - 1) / a.TH;
     a.lbo_a = (uint32_t)(128 + 8 / G) * 16;
+    a.mul_TW = fast_div_mul((uint32_t)a.TW);
+    a.mul_tiles_x = fast_div_mul((uint32_t)a.tiles_x);
+    a.mul_tiles = fast_div_mul((uint32_t)(a.tiles_x * a.tiles_y));
 }
 inline size_t tc_dw2d_smem_bytes(const TcDw2dArgs &a) {
     return (size_t)a.PH * a.PW * a.C * 2 + (size_t)(a.C / 8) * a.lbo_a + (size_t)a.C * a.N * 2 + 128;
@@ -62,8 +66,8 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
     unsigned char *sA = smem + (size_t)PH * PW * pix;
     unsigned char *sB = sA + (size_t)G * lbo_a;
     const int tiles = a.tiles_x * a.tiles_y;
-    const int b = blockIdx.x / tiles, trem = blockIdx.x - b * tiles;
-    const int ty0 = trem / a.tiles_x;
+    const int b = fast_div((int)blockIdx.x, a.mul_tiles), trem = blockIdx.x - b * tiles;
+    const int ty0 = fast_div(trem, a.mul_tiles_x);
     const int oy0 = ty0 * a.TH, ox0 = (trem - ty0 * a.tiles_x) * a.TW;
     const int iy0 = oy0 * a.S - 1, ix0 = ox0 * a.S - 1;          // input coordinates of staged (0, 0)
 
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
         const int items = (a.TH >> 1) * a.TW << lg;
         for (int it = tid; it < items; it += TC_THREADS) {
             const int g = it & (G - 1), rest = it >> lg;
-            const int typ = rest / a.TW, tx = rest - typ * a.TW;
+            const int typ = fast_div(rest, a.mul_TW), tx = rest - typ * a.TW;
             const int ty = typ * 2;
             float acc0[8], acc1[8];
             {
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
         const int items = rows << lg;
         for (int it = tid; it < items; it += TC_THREADS) {
             const int g = it & (G - 1), r = it >> lg;
-            const int ty = r / a.TW, tx = r - ty * a.TW;
+            const int ty = fast_div(r, a.mul_TW), tx = r - ty * a.TW;
             float acc[8];
             {
                 const float4 b0 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g * 8]), b1 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g * 8 + 4]);
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
     tc::tc_fence_after();
     {
         const int r = (warp & 3) * 32 + lane;
-        const int ty = r / a.TW, tx = r - ty * a.TW;
+        const int ty = fast_div(r, a.mul_TW), tx = r - ty * a.TW;
         const int oy = oy0 + ty, ox = ox0 + tx;
         const bool ok = r < rows && oy < a.OH && ox < a.OW;
         TcOut o{a.out, a.N, a.N, 1, nullptr, 0, 0};

@@ -17,6 +17,7 @@ struct TcDw2dArgsI8 {
     int N, Kpad;            // Kpad = C rounded up to 32
     int TH, TW, tiles_x, tiles_y, PH, PW;
     uint32_t lbo_a;
+    uint32_t mul_TW;        // fast_div multiplier (tc_dw2d_i8_finish)
     const int8_t *wimg;     // [Kpad/16][N][16]
     const float *mult, *bq; // [N]
     const float *dw_w;      // [9][C] folded depthwise weights * s_in
@@ -31,6 +32,7 @@ inline void tc_dw2d_i8_finish(TcDw2dArgsI8 &a) {
     a.tiles_x = (a.OW + a.TW - 1) / a.TW;
     a.tiles_y = (a.OH + a.TH - 1) / a.TH;
     a.lbo_a = 129 * 16;
+    a.mul_TW = fast_div_mul((uint32_t)a.TW);
 }
 inline size_t tc_dw2d_i8_smem_bytes(const TcDw2dArgsI8 &a) {
     return (size_t)a.PH * a.PW * a.C + (size_t)(a.Kpad / 16) * a.lbo_a + (size_t)a.Kpad * a.N + 128 + 16;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tc_dwpw_2d_i8(const TcDw2dArg
         const int items = (a.TH >> 1) * a.TW << lh;
         for (int it = tid; it < items; it += TC_THREADS) {
             const int hg = it & (H8 - 1), rest = it >> lh;
-            const int typ = rest / a.TW, tx = rest - typ * a.TW;
+            const int typ = fast_div(rest, a.mul_TW), tx = rest - typ * a.TW;
             const int ty = typ * 2, c0 = hg * 8;
             float acc0[8], acc1[8];
 #pragma unroll
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tc_dwpw_2d_i8(const TcDw2dArg
         const int items = rows << lh;
         for (int it = tid; it < items; it += TC_THREADS) {
             const int hg = it & (H8 - 1), r = it >> lh;
-            const int ty = r / a.TW, tx = r - ty * a.TW;
+            const int ty = fast_div(r, a.mul_TW), tx = r - ty * a.TW;
             const int c0 = hg * 8;
             float acc[8];
 #pragma unroll
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tc_dwpw_2d_i8(const TcDw2dArg
     tc::tc_fence_after();
     {
         const int r = (warp & 3) * 32 + lane;
-        const int ty = r / a.TW, tx = r - ty * a.TW;
+        const int ty = fast_div(r, a.mul_TW), tx = r - ty * a.TW;
         const int oy = oy0 + ty, ox = ox0 + tx;
         const bool ok = r < rows && oy < a.OH && ox < a.OW;
         TcOutI8 o{a.out, a.N, a.N, 1, nullptr, 0, 0};
