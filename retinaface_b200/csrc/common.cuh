@@ -56,6 +56,7 @@ template <> __device__ __forceinline__ __half from_f<__half>(float x) { return _
 // the identity).  An integer division by a run-time value costs ~25 instructions; the 2-D depthwise kernels did five per thread.
 inline uint32_t fast_div_mul(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); }
 __device__ __forceinline__ int fast_div(int n, uint32_t mul) { return mul ? (int)__umulhi((uint32_t)n, mul) : n; }
+__device__ __forceinline__ int fast_floor_div(int n, int d, uint32_t mul) { return n >= 0 ? fast_div(n, mul) : -fast_div(-n + d - 1, mul); }
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------
 // Every kernel of the forward pass is launched with cudaLaunchAttributeProgrammaticStreamSerialization:

@@ -73,7 +73,9 @@ std::vector<__half> pack_tc_weights(const std::vector<const FoldedConv *> &cs, s
     return img;
 }
 
-void launch_tc_conv(const TcConvArgs &a, cudaStream_t s) {
+void launch_tc_conv(const TcConvArgs &a_in, cudaStream_t s) {
+    TcConvArgs a = a_in;
+    a.mul_Wp = fast_div_mul((uint32_t)a.Wp); a.mul_Hp = fast_div_mul((uint32_t)a.Hp); a.mul_H = fast_div_mul((uint32_t)a.H);
     const long P = (long)a.nimg * a.Hp * a.Wp;
     const unsigned grid = (unsigned)((P + 127) / 128);
     const size_t smem = tc_conv_smem_bytes(a);
@@ -84,7 +86,10 @@ void launch_tc_conv(const TcConvArgs &a, cudaStream_t s) {
         default: if (a.up) CK_L(k_tc_conv_staged<256, true>, dim3(grid), dim3(TC_THREADS), smem, s, a); else CK_L(k_tc_conv_staged<256, false>, dim3(grid), dim3(TC_THREADS), smem, s, a); break;
     }
 }
-void launch_tc_dwpw(const TcDwArgs &a, int nsplit, cudaStream_t s) {
+void launch_tc_dwpw(const TcDwArgs &a_in, int nsplit, cudaStream_t s) {
+    TcDwArgs a = a_in;
+    a.mul_Wp = fast_div_mul((uint32_t)a.Wp); a.mul_Hp = fast_div_mul((uint32_t)a.Hp);
+    a.mul_OW = fast_div_mul((uint32_t)a.OW); a.mul_OH = fast_div_mul((uint32_t)a.OH);
     const long M = (long)a.nimg * a.OH * a.OW;
     dim3 grid((unsigned)((M + a.rows - 1) / a.rows), nsplit);
     const size_t smem = tc_dw_smem_bytes(a);

@@ -48,7 +48,9 @@ QWeights pack_tc_weights_i8(const std::vector<const FoldedConv *> &cs, float s_i
     return q;
 }
 
-void launch_tc_conv_i8(const TcConvArgsI8 &a, cudaStream_t s) {
+void launch_tc_conv_i8(const TcConvArgsI8 &a_in, cudaStream_t s) {
+    TcConvArgsI8 a = a_in;
+    a.mul_Wp = fast_div_mul((uint32_t)a.Wp); a.mul_Hp = fast_div_mul((uint32_t)a.Hp); a.mul_H = fast_div_mul((uint32_t)a.H);
     const long P = (long)a.nimg * a.Hp * a.Wp;
     const dim3 grid((unsigned)((P + 127) / 128));
     const size_t smem = tc_conv_i8_smem_bytes(a);
@@ -72,7 +74,10 @@ void launch_tc_dwpw_2d_i8(const TcDw2dArgsI8 &a, cudaStream_t s) {
     }
 }
 
-void launch_tc_dwpw_i8(const TcDwArgsI8 &a, int nsplit, cudaStream_t s) {
+void launch_tc_dwpw_i8(const TcDwArgsI8 &a_in, int nsplit, cudaStream_t s) {
+    TcDwArgsI8 a = a_in;
+    a.mul_Wp = fast_div_mul((uint32_t)a.Wp); a.mul_Hp = fast_div_mul((uint32_t)a.Hp);
+    a.mul_OW = fast_div_mul((uint32_t)a.OW); a.mul_OH = fast_div_mul((uint32_t)a.OH);
     const long M = (long)a.nimg * a.OH * a.OW;
     const dim3 grid((unsigned)((M + a.rows - 1) / a.rows), nsplit);
     const size_t smem = tc_dw_i8_smem_bytes(a);

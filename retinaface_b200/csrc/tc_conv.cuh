@@ -140,6 +140,7 @@ struct TcConvArgs {
     int N;                  // output channels (multiple of 16, <= 256)
     int Wp, Hp;             // padded geometry: taps==9 ? (W+2, H+1) : (W, H)
     int R;                  // staged positions per tile (odd): 128 + 2*(Wp+1) for 3x3, 129 for 1x1
+    uint32_t mul_Wp, mul_Hp, mul_H;   // fast_div multipliers (set by the launch helper)
     const __half *wimg;     // B image [K/8][N][8] halfs, K = taps*Cin ordered (tap, cin)
     const float *bias;      // [N]
     TcOut out;
@@ -234,10 +235,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     // position table, one warp per padded row (no per-position divisions): p = prow * Wp + xx
     {
         const int lane = tid & 31;
-        const int prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;          // floor
-        const int prow1 = (lo + a.R - 1) / a.Wp;
+        const int prow0 = fast_floor_div(lo, a.Wp, a.mul_Wp);          // floor
+        const int prow1 = fast_div(lo + a.R - 1, a.mul_Wp);
         for (int prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
-            const int b = prow >= 0 ? (int)(prow / a.Hp) : -1;
+            const int b = prow >= 0 ? fast_div(prow, a.mul_Hp) : -1;
             const int yy = prow >= 0 ? (int)(prow - b * a.Hp) : 0;
             const bool rowok = prow >= 0 && b < a.nimg && yy < a.H;
             for (int xx = lane; xx < a.Wp; xx += 32) {
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
             const int c0 = g * 8;
             const int yx = s_yx[pl];
             const int x = yx & 0xfff, gy = yx >> 12;             // gy = b*H + y
-            const int b = gy / a.H, y = gy - b * a.H;            // one division (vs three): b changes at most once per tile
+            const int b = fast_div(gy, a.mul_H), y = gy - b * a.H;            // one division (vs three): b changes at most once per tile
             unsigned char *slot = sS + (size_t)g * lbo_s + (size_t)pl * 16;
             // packed FP16 arithmetic (HFMA2): the sum of <= 5 terms is stored as FP16 anyway; the reference's
             // deconvolution weights (1/16, 3/16, 9/16) are exact in FP16
@@ -393,6 +394,7 @@ struct TcDwArgs {
     int rows;               // output pixels per CTA (64 | 128)
     int Wp, Hp;             // IW + 2, IH + 1
     int Rmax;               // staged positions, upper bound over tiles (odd)
+    uint32_t mul_Wp, mul_Hp, mul_OW, mul_OH;   // fast_div multipliers (set by the launch helper)
     const __half *wimg;     // slice s at s * Kpad * N halfs: [Kpad/8][N][8]
     const float *bias;      // [Ntotal]
     const float *dw_w, *dw_b;   // [9][C], [C]
@@ -423,7 +425,8 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
     const int tid = threadIdx.x, warp = tid >> 5;
     const int G = a.C >> 3;
     const int GA = a.Kpad >> 3;          // A groups (== G except the Cin = 8 layer: 2, second one zero)
-    const int g_own = tid % GA;
+    const int lgGA = 31 - __clz(GA);          // Kpad / 8 (16) is a power of two
+    const int g_own = tid & (GA - 1);
     // the staged range is PIXEL-major, [position][C] (a copy of the NHWC pixels): consecutive cp.async lanes write consecutive
     // shared addresses, and the stencil's lanes -- channel group fastest -- read consecutive 16-byte pieces
     const int pix = a.C * 2;
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
     const int m0 = blockIdx.x * a.rows;
     const int mlast = min(m0 + a.rows, M) - 1;
     auto centre = [&](int m) -> int {
-        const int ox = (int)(m % a.OW), oy = (int)((m / a.OW) % a.OH), b = (int)(m / (a.OW * a.OH));
+        const int q = fast_div(m, a.mul_OW), ox = m - q * a.OW, b = fast_div(q, a.mul_OH), oy = q - b * a.OH;
         return (b * a.Hp + oy * a.S) * a.Wp + ox * a.S + 1;
     };
     const int lo = centre(m0) - a.Wp - 1;
@@ -468,10 +471,10 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
     }
     {
         const int lane = tid & 31;
-        const int prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;          // floor
-        const int prow1 = (lo + R - 1) / a.Wp;
+        const int prow0 = fast_floor_div(lo, a.Wp, a.mul_Wp);          // floor
+        const int prow1 = fast_div(lo + R - 1, a.mul_Wp);
         for (int prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
-            const int b = prow >= 0 ? (int)(prow / a.Hp) : -1;
+            const int b = prow >= 0 ? fast_div(prow, a.mul_Hp) : -1;
             const int yy = prow >= 0 ? (int)(prow - b * a.Hp) : 0;
             const bool rowok = prow >= 0 && b < a.nimg && yy < a.IH;
             for (int xx = lane; xx < a.Wp; xx += 32) {
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
     // Each thread owns ONE 8-channel group (TC_THREADS % GA == 0) and walks the tile's rows, so its 72
     // folded depthwise weights + 8 biases live in registers (loaded before pdl_wait, above).
     if (g_own < G) {
-        for (int r = tid / GA; r < a.rows; r += TC_THREADS / GA) {
+        for (int r = tid >> lgGA; r < a.rows; r += TC_THREADS >> lgGA) {
             const int cp = s_cpos[r];
             if (cp < 0) continue;            // rows beyond M (last tile): never read back
             float acc[8];
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
             *reinterpret_cast<uint4 *>(sA + (size_t)g_own * lbo_a + (size_t)r * 16) = o.v;
         }
     } else {                                  // K padding group of the Cin = 8 layer: zeros
-        for (int r = tid / GA; r < a.rows; r += TC_THREADS / GA)
+        for (int r = tid >> lgGA; r < a.rows; r += TC_THREADS >> lgGA)
             *reinterpret_cast<uint4 *>(sA + (size_t)g_own * lbo_a + (size_t)r * 16) = make_uint4(0, 0, 0, 0);
     }
     tc::fence_async_smem();

@@ -101,6 +101,7 @@ struct TcConvArgsI8 {
     int taps;               // 1 | 9
     int N;
     int Wp, Hp, R;          // as TcConvArgs
+    uint32_t mul_Wp, mul_Hp, mul_H;   // fast_div multipliers (set by the launch helper)
     const int8_t *wimg;     // [taps * GS][N][16] int8, GS = max(Cin/16, 2) groups per tap (zero padded)
     const float *mult, *bq; // [N]: s_in*s_w[n]/s_out(n), b'[n]/s_out(n)
     TcOutI8 out;
@@ -154,10 +155,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged_i8(const TcConvAr
     if (UPADD) for (int i = tid; i < a.Cin * 16; i += TC_THREADS) s_uw[i] = a.up_wq[i];
     {
         const int lane = tid & 31;
-        const int prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;
-        const int prow1 = (lo + a.R - 1) / a.Wp;
+        const int prow0 = fast_floor_div(lo, a.Wp, a.mul_Wp);
+        const int prow1 = fast_div(lo + a.R - 1, a.mul_Wp);
         for (int prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
-            const int b = prow >= 0 ? (int)(prow / a.Hp) : -1;
+            const int b = prow >= 0 ? fast_div(prow, a.mul_Hp) : -1;
             const int yy = prow >= 0 ? (int)(prow - b * a.Hp) : 0;
             const bool rowok = prow >= 0 && b < a.nimg && yy < a.H;
             for (int xx = lane; xx < a.Wp; xx += 32) {
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged_i8(const TcConvAr
             const int c0 = g * 16;
             const int yx = s_yx[pl];
             const int x = yx & 0xfff, gy = yx >> 12;
-            const int b = gy / a.H, y = gy - b * a.H;
+            const int b = fast_div(gy, a.mul_H), y = gy - b * a.H;
             unsigned char *slot = sS + (size_t)g * lbo_s + (size_t)pl * 16;
             float acc[16];
             tc::unpack16(*reinterpret_cast<const uint4 *>(slot), acc);
@@ -293,6 +294,7 @@ struct TcDwArgsI8 {
     int C, nimg, IH, IW, OH, OW, S;
     int N, Ntotal, Kpad;    // Kpad = C rounded up to 32
     int rows, Wp, Hp, Rmax;
+    uint32_t mul_Wp, mul_Hp, mul_OW, mul_OH;   // fast_div multipliers (set by the launch helper)
     const int8_t *wimg;     // slice s at s * Kpad * N bytes: [Kpad/16][N][16]
     const float *mult, *bq; // [Ntotal]
     const float *dw_w;      // [9][C] folded depthwise weights * s_in
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
     const int m0 = blockIdx.x * a.rows;
     const int mlast = min(m0 + a.rows, M) - 1;
     auto centre = [&](int m) -> int {
-        const int ox = (int)(m % a.OW), oy = (int)((m / a.OW) % a.OH), b = (int)(m / (a.OW * a.OH));
+        const int q = fast_div(m, a.mul_OW), ox = m - q * a.OW, b = fast_div(q, a.mul_OH), oy = q - b * a.OH;
         return (b * a.Hp + oy * a.S) * a.Wp + ox * a.S + 1;
     };
     const int lo = centre(m0) - a.Wp - 1;
@@ -365,10 +367,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_dwpw_staged_i8(const TcDwA
     }
     {
         const int lane = tid & 31;
-        const int prow0 = (lo >= 0 ? lo : lo - (a.Wp - 1)) / a.Wp;
-        const int prow1 = (lo + R - 1) / a.Wp;
+        const int prow0 = fast_floor_div(lo, a.Wp, a.mul_Wp);
+        const int prow1 = fast_div(lo + R - 1, a.mul_Wp);
         for (int prow = prow0 + warp; prow <= prow1; prow += TC_THREADS / 32) {
-            const int b = prow >= 0 ? (int)(prow / a.Hp) : -1;
+            const int b = prow >= 0 ? fast_div(prow, a.mul_Hp) : -1;
             const int yy = prow >= 0 ? (int)(prow - b * a.Hp) : 0;
             const bool rowok = prow >= 0 && b < a.nimg && yy < a.IH;
             for (int xx = lane; xx < a.Wp; xx += 32) {
