@@ -58,6 +58,22 @@ inline uint32_t fast_div_mul(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((((ui
 __device__ __forceinline__ int fast_div(int n, uint32_t mul) { return mul ? (int)__umulhi((uint32_t)n, mul) : n; }
 __device__ __forceinline__ int fast_floor_div(int n, int d, uint32_t mul) { return n >= 0 ? fast_div(n, mul) : -fast_div(-n + d - 1, mul); }
 
+// ---- depthwise inner product without conversions: acc[i] += x[i] * w[i] for 8 packed FP16 pairs with FHFMA (fma.rn.f32.f16:
+// FP16 x FP16 multiplicands, exact product, FP32 addend and result -- one instruction per MAC where cvt + FFMA took two).
+// The depthwise weights are therefore FP16-rounded, like every other weight of the FP16 engine; the bias stays FP32.
+__device__ __forceinline__ void fhfma2(float &a0, float &a1, uint32_t x2, uint32_t w2) {
+    asm("{\n\t.reg .f16 xl, xh, wl, wh;\n\tmov.b32 {xl, xh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\tfma.rn.f32.f16 %0, xl, wl, %0;\n\tfma.rn.f32.f16 %1, xh, wh, %1;\n\t}"
+        : "+f"(a0), "+f"(a1) : "r"(x2), "r"(w2));
+}
+__device__ __forceinline__ void fhfma8(float (&acc)[8], const uint4 &x, const uint4 &w) {
+    fhfma2(acc[0], acc[1], x.x, w.x); fhfma2(acc[2], acc[3], x.y, w.y); fhfma2(acc[4], acc[5], x.z, w.z); fhfma2(acc[6], acc[7], x.w, w.w);
+}
+__device__ __forceinline__ uint4 pack_half8(const float4 &a, const float4 &b) {
+    const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w), h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+    return make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1), *reinterpret_cast<const uint32_t *>(&h2),
+                      *reinterpret_cast<const uint32_t *>(&h3));
+}
+
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------
 // Every kernel of the forward pass is launched with cudaLaunchAttributeProgrammaticStreamSerialization:
 // its CTAs may start while the previous kernel drains.  pdl_trigger() lets the NEXT kernel start its

@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
     __shared__ uint32_t s_tmem;
     __shared__ int s_cpos[128];          // GEMM row -> staged index of its stencil centre, -1 = no output
     __shared__ float s_bias[256];
-    __shared__ __align__(16) float s_dw[WREG ? 4 : 10 * 64];   // !WREG: [tap][C] weights, [9] = bias (C <= 64)
+    __shared__ __align__(16) __half s_dwh[WREG ? 8 : 9 * 64];  // !WREG: [tap][C] FP16 weights (C <= 64)
+    __shared__ __align__(16) float s_dwb[WREG ? 4 : 64];       // !WREG: [C] bias
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int G = a.C >> 3;
@@ -457,17 +458,19 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
     if (warp == 1) tc::tmem_alloc<NT>(&s_tmem);
     pdl_trigger();
     if (tid < a.N) s_bias[tid] = a.bias[blockIdx.y * a.N + tid];
-    float wreg[WREG ? 10 : 1][8];        // [tap][channel] folded depthwise weights, [9] = bias
+    uint4 wreg[WREG ? 9 : 1];            // [tap] 8 packed FP16 depthwise weights of this thread's channel group (fhfma8)
+    float breg[8];                       // its 8 biases
     if (!WREG) {
-        for (int i = tid; i < 10 * a.C; i += TC_THREADS) s_dw[i] = i < 9 * a.C ? a.dw_w[i] : a.dw_b[i - 9 * a.C];
+        for (int i = tid; i < 9 * a.C; i += TC_THREADS) s_dwh[i] = __float2half_rn(a.dw_w[i]);
+        for (int i = tid; i < a.C; i += TC_THREADS) s_dwb[i] = a.dw_b[i];
     } else if (g_own < G) {
 #pragma unroll
-        for (int t = 0; t < (WREG ? 10 : 1); t++) {
-            const float *src = (t < 9 ? a.dw_w + t * a.C : a.dw_b) + g_own * 8;
-            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(src)), w1 = __ldg(reinterpret_cast<const float4 *>(src) + 1);
-            wreg[t][0] = w0.x; wreg[t][1] = w0.y; wreg[t][2] = w0.z; wreg[t][3] = w0.w;
-            wreg[t][4] = w1.x; wreg[t][5] = w1.y; wreg[t][6] = w1.z; wreg[t][7] = w1.w;
+        for (int t = 0; t < (WREG ? 9 : 1); t++) {
+            const float *src = a.dw_w + t * a.C + g_own * 8;
+            wreg[t] = pack_half8(__ldg(reinterpret_cast<const float4 *>(src)), __ldg(reinterpret_cast<const float4 *>(src) + 1));
         }
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(a.dw_b + g_own * 8)), b1 = __ldg(reinterpret_cast<const float4 *>(a.dw_b + g_own * 8) + 1);
+        breg[0] = b0.x; breg[1] = b0.y; breg[2] = b0.z; breg[3] = b0.w; breg[4] = b1.x; breg[5] = b1.y; breg[6] = b1.z; breg[7] = b1.w;
     }
     {
         const int lane = tid & 31;
@@ -508,27 +511,18 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
             float acc[8];
             if (WREG) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] = wreg[WREG ? 9 : 0][i];
+                for (int i = 0; i < 8; i++) acc[i] = breg[i];
             } else {
-                const float4 b0 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g_own * 8]), b1 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g_own * 8 + 4]);
+                const float4 b0 = *reinterpret_cast<const float4 *>(&s_dwb[g_own * 8]), b1 = *reinterpret_cast<const float4 *>(&s_dwb[g_own * 8 + 4]);
                 acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
             }
             const unsigned char *base = sS + cp * pix + g_own * 16;
 #pragma unroll
             for (int t = 0; t < 9; t++) {
                 const int shift = (t / 3 - 1) * a.Wp + (t % 3 - 1);
-                Vec8<__half> x;
-                x.v = *reinterpret_cast<const uint4 *>(base + shift * pix);
-                float f[8];
-                x.to_float(f);
-                if (WREG) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) acc[i] = fmaf(f[i], wreg[WREG ? t : 0][i], acc[i]);
-                } else {
-                    const float4 w0 = *reinterpret_cast<const float4 *>(&s_dw[t * a.C + g_own * 8]), w1 = *reinterpret_cast<const float4 *>(&s_dw[t * a.C + g_own * 8 + 4]);
-                    acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]); acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
-                    acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]); acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
-                }
+                const uint4 x = *reinterpret_cast<const uint4 *>(base + shift * pix);
+                if (WREG) fhfma8(acc, x, wreg[WREG ? t : 0]);
+                else fhfma8(acc, x, *reinterpret_cast<const uint4 *>(&s_dwh[t * a.C + g_own * 8]));
             }
 #pragma unroll
             for (int i = 0; i < 8; i++) acc[i] = fmaxf(acc[i], 0.f);

@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
     __shared__ __align__(8) uint64_t bar_b, bar_done;
     __shared__ uint32_t s_tmem;
     __shared__ float s_bias[256];
-    __shared__ __align__(16) float s_dw[10 * 64];     // [tap][C] folded depthwise weights, [9] = bias
+    __shared__ __align__(16) __half s_dwh[9 * 64];    // [tap][C] folded depthwise weights, FP16 (fhfma8)
+    __shared__ __align__(16) float s_dwb[64];         // [C] bias
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = a.C >> 3, lg = 31 - __clz(G);
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
     if (warp == 1) tc::tmem_alloc<NT>(&s_tmem);
     pdl_trigger();
     if (tid < a.N) s_bias[tid] = a.bias[tid];
-    for (int i = tid; i < 10 * a.C; i += TC_THREADS) s_dw[i] = i < 9 * a.C ? a.dw_w[i] : a.dw_b[i - 9 * a.C];
+    for (int i = tid; i < 9 * a.C; i += TC_THREADS) s_dwh[i] = __float2half_rn(a.dw_w[i]);
+    if (tid < a.C) s_dwb[tid] = a.dw_b[tid];
     pdl_wait();
     // ---- stage the (PH x PW) input window: one warp per staged row, lanes over (column, channel group) -- a staged row
     // is PW*C contiguous halfs of the input (16 B per lane, fully coalesced); outside the map: zero fill ------------------
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
             const int ty = typ * 2;
             float acc0[8], acc1[8];
             {
-                const float4 b0 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g * 8]), b1 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g * 8 + 4]);
+                const float4 b0 = *reinterpret_cast<const float4 *>(&s_dwb[g * 8]), b1 = *reinterpret_cast<const float4 *>(&s_dwb[g * 8 + 4]);
                 acc0[0] = b0.x; acc0[1] = b0.y; acc0[2] = b0.z; acc0[3] = b0.w; acc0[4] = b1.x; acc0[5] = b1.y; acc0[6] = b1.z; acc0[7] = b1.w;
 #pragma unroll
                 for (int i = 0; i < 8; i++) acc1[i] = acc0[i];
@@ -125,20 +127,9 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
             for (int ry = 0; ry < 4; ry++) {
 #pragma unroll
                 for (int kx = 0; kx < 3; kx++) {
-                    Vec8<__half> x;
-                    x.v = *reinterpret_cast<const uint4 *>(base + (ry * PW + kx) * pix);
-                    float f[8];
-                    x.to_float(f);
-                    if (ry < 3) {        // output row ty: kernel row ry
-                        const float4 w0 = *reinterpret_cast<const float4 *>(&s_dw[(ry * 3 + kx) * a.C + g * 8]), w1 = *reinterpret_cast<const float4 *>(&s_dw[(ry * 3 + kx) * a.C + g * 8 + 4]);
-                        acc0[0] = fmaf(f[0], w0.x, acc0[0]); acc0[1] = fmaf(f[1], w0.y, acc0[1]); acc0[2] = fmaf(f[2], w0.z, acc0[2]); acc0[3] = fmaf(f[3], w0.w, acc0[3]);
-                        acc0[4] = fmaf(f[4], w1.x, acc0[4]); acc0[5] = fmaf(f[5], w1.y, acc0[5]); acc0[6] = fmaf(f[6], w1.z, acc0[6]); acc0[7] = fmaf(f[7], w1.w, acc0[7]);
-                    }
-                    if (ry > 0) {        // output row ty + 1: kernel row ry - 1
-                        const float4 w0 = *reinterpret_cast<const float4 *>(&s_dw[((ry - 1) * 3 + kx) * a.C + g * 8]), w1 = *reinterpret_cast<const float4 *>(&s_dw[((ry - 1) * 3 + kx) * a.C + g * 8 + 4]);
-                        acc1[0] = fmaf(f[0], w0.x, acc1[0]); acc1[1] = fmaf(f[1], w0.y, acc1[1]); acc1[2] = fmaf(f[2], w0.z, acc1[2]); acc1[3] = fmaf(f[3], w0.w, acc1[3]);
-                        acc1[4] = fmaf(f[4], w1.x, acc1[4]); acc1[5] = fmaf(f[5], w1.y, acc1[5]); acc1[6] = fmaf(f[6], w1.z, acc1[6]); acc1[7] = fmaf(f[7], w1.w, acc1[7]);
-                    }
+                    const uint4 x = *reinterpret_cast<const uint4 *>(base + (ry * PW + kx) * pix);
+                    if (ry < 3) fhfma8(acc0, x, *reinterpret_cast<const uint4 *>(&s_dwh[(ry * 3 + kx) * a.C + g * 8]));         // output row ty: kernel row ry
+                    if (ry > 0) fhfma8(acc1, x, *reinterpret_cast<const uint4 *>(&s_dwh[((ry - 1) * 3 + kx) * a.C + g * 8]));   // output row ty + 1: kernel row ry - 1
                 }
             }
 #pragma unroll
@@ -157,19 +148,13 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
             const int ty = fast_div(r, a.mul_TW), tx = r - ty * a.TW;
             float acc[8];
             {
-                const float4 b0 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g * 8]), b1 = *reinterpret_cast<const float4 *>(&s_dw[9 * a.C + g * 8 + 4]);
+                const float4 b0 = *reinterpret_cast<const float4 *>(&s_dwb[g * 8]), b1 = *reinterpret_cast<const float4 *>(&s_dwb[g * 8 + 4]);
                 acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
             }
             const unsigned char *base = sS + (ty * a.S * PW + tx * a.S) * pix + g * 16;
 #pragma unroll
             for (int t = 0; t < 9; t++) {
-                Vec8<__half> x;
-                x.v = *reinterpret_cast<const uint4 *>(base + ((t / 3) * PW + (t % 3)) * pix);
-                float f[8];
-                x.to_float(f);
-                const float4 w0 = *reinterpret_cast<const float4 *>(&s_dw[t * a.C + g * 8]), w1 = *reinterpret_cast<const float4 *>(&s_dw[t * a.C + g * 8 + 4]);
-                acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]); acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
-                acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]); acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+                fhfma8(acc, *reinterpret_cast<const uint4 *>(base + ((t / 3) * PW + (t % 3)) * pix), *reinterpret_cast<const uint4 *>(&s_dwh[t * a.C + g * 8]));
             }
 #pragma unroll
             for (int i = 0; i < 8; i++) acc[i] = fmaxf(acc[i], 0.f);
