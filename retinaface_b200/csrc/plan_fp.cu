@@ -249,6 +249,7 @@ void plan_conv_legacy(Builder &B, const std::string &sname, std::vector<const Fo
     size_t oimg = B.add_weights_h(img), ob = B.add_weights(bias);
     const int N = (int)bias.size(), cin = cs[0]->cin, ks = cs[0]->k;
     size_t oup = tup >= 0 ? B.add_weights(m.up_w[up_which]) : 0;
+    if (cin & (cin - 1)) throw PlanFail{RF_ERR_UNSUPPORTED, fmt("convolution %s: %d input channels (the tensor-core kernels index by shifts: powers of two only)", sname.c_str(), cin)};
     TcConvArgs probe{};
     probe.Cin = cin; probe.taps = ks * ks; probe.N = N; probe.R = (ks == 3 ? 128 + 2 * (iw + 3) : 128) | 1;
     if (tup >= 0) { probe.up = reinterpret_cast<const __half *>(1); probe.Cmax = (((probe.R / (iw + 2) + 2) / 2 + 3) * (iw / 2)) | 1; }

@@ -280,22 +280,27 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     {
         // through registers: LDG.128 (coalesced) then STS.128 -- with R odd the 8 lanes of a quarter warp (8 groups of one
         // pixel) hit 8 different bank groups, so the store costs the ideal 4 wavefronts per warp instead of cp.async's 32
+        // TC_THREADS is a multiple of G: a thread keeps ONE channel group and walks positions p0, p0 + pstep, ... -- source and
+        // destination addresses are a per-thread base plus a multiple of the position (32-bit adds only)
         constexpr int UNR = 4;
-        for (int it0 = tid; it0 < a.R * G; it0 += TC_THREADS * UNR) {
+        const int g = tid & (G - 1), p0 = tid >> lg, pstep = TC_THREADS >> lg;
+        const __half *src_g = a.in + g * 8;
+        unsigned char *dst_g = sS + (uint32_t)g * lbo_s;
+        for (int pb = p0; pb < a.R; pb += pstep * UNR) {
             uint4 v[UNR];
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
-                const int it = it0 + u * TC_THREADS;
+                const int p = pb + u * pstep;
                 v[u] = make_uint4(0, 0, 0, 0);
-                if (it < a.R * G) {
-                    const int off = s_off[it >> lg];
-                    if (off >= 0) v[u] = __ldcg(reinterpret_cast<const uint4 *>(a.in + off + (it & (G - 1)) * 8));     // L2 only, like cp.async.cg
+                if (p < a.R) {
+                    const int off = s_off[p];
+                    if (off >= 0) v[u] = __ldcg(reinterpret_cast<const uint4 *>(src_g + off));     // L2 only, like cp.async.cg
                 }
             }
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
-                const int it = it0 + u * TC_THREADS;
-                if (it < a.R * G) *reinterpret_cast<uint4 *>(sS + (size_t)(it & (G - 1)) * lbo_s + (size_t)(it >> lg) * 16) = v[u];
+                const int p = pb + u * pstep;
+                if (p < a.R) *reinterpret_cast<uint4 *>(dst_g + (uint32_t)p * 16u) = v[u];
             }
         }
     }
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tc_conv_staged(const TcConvArgs 
     {
         const int r = (warp & 3) * 32 + (tid & 31);
         const int off = s_off[(int)(m0 - lo) + r];               // element offset / Cin == output pixel index
-        tc_epilogue(tmem, a.N, s_bias, a.out, off >= 0 ? (off / a.Cin) : -1, 0);
+        tc_epilogue(tmem, a.N, s_bias, a.out, off >= 0 ? (off >> (31 - __clz(a.Cin))) : -1, 0);   // Cin is a power of two (plan_conv_legacy checks)
     }
     tc::tc_fence_before();
     __syncthreads();

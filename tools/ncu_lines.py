@@ -9,6 +9,7 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    want = sys.argv[3] if len(sys.argv) > 3 else None      # substring of the function name (default: the first kernel)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
     fpath, fn, first_fn = None, None, None
     lines = {}
@@ -19,7 +20,8 @@ def main():
             fpath = row[1].split("/")[-1]
         elif row[0] == "Function Name":
             fn = row[1]
-            first_fn = first_fn or fn
+            if want is None or want in fn:
+                first_fn = first_fn or fn
         elif row[0].isdigit() and fn == first_fn and len(row) > 7:
             key = (fpath, int(row[0]))
             e = lines.setdefault(key, [0, 0, row[1].strip()])
