@@ -485,11 +485,13 @@ cudaError_t tile_init() {
 
 // RF_TILE_MASK bits: which parts of the FP16 plan run as tile chains; the others use the round-1 kernels.
 enum { TM_A = 1, TM_B = 2, TM_C = 4, TM_D = 8, TM_E = 16, TM_AGGR = 32, TM_SSH = 64, TM_HEAD = 128, TM_NMS = 256, TM_ALL = 511 };
-// Measured on a B200 (profiles/README.md, tools/mask_sweep.py): with ONE execution context (a single forward at a time: the
-// blocking / latency mode) the convolution chains + chain B shorten the step; with several contexts overlapping batches
-// (throughput mode) the GPU is already kept busy by batch-level parallelism and what counts is SM-time per step, where the
-// short round-1 kernels (2-4 CTAs per SM) still win -- there only the fused decode + NMS tail is taken over.
-constexpr unsigned TM_LATENCY = TM_B | TM_AGGR | TM_SSH | TM_HEAD | TM_NMS;
+// Measured on a B200 (profiles/r02_mask_sweep.txt, tools/mask_sweep.py): with ONE execution context (a single forward at a
+// time: the blocking / latency mode) the SSH + predictor + NMS chains (and, at batch 1-2, the merge+aggr chains) shorten or
+// tie the step; with several contexts overlapping batches (throughput mode) what counts is SM time per step, where the
+// per-layer kernels win -- there only the fused decode + NMS tail is taken over.  The backbone chains (depthwise on tensor
+// cores) lose to the per-layer kernels since those run their stencils on FHFMA.
+constexpr unsigned TM_LATENCY = TM_SSH | TM_HEAD | TM_NMS;
+constexpr unsigned TM_LATENCY_SMALL = TM_AGGR | TM_SSH | TM_HEAD | TM_NMS;      // max_batch <= 2
 constexpr unsigned TM_THROUGHPUT = 0;
 
 // builds the plan for one mask; false: the predictors could not be fused at all three levels (the caller retries without)
@@ -698,10 +700,12 @@ static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
 }
 
 void build_plan_tiles(rf_handle h) {
-    // the chain plan pays off for one forward at a time AND small batches (profiles/r02_mask_sweep.txt: batch 1 / 8, one
-    // context: 118.8 / 178.6 us against 124.5 / 184.1 us; batch 32: 456 against 420 us -- there every kernel fills the GPU)
+    // the chain plan pays off for one forward at a time AND small batches (profiles/r02_mask_sweep.txt: one context, batch 1:
+    // 107.7 us against 113.6 us per-layer; batch 8: 165.2 against 165.7 us; batch 32: 456 against 420 us -- there every kernel
+    // fills the GPU)
     const bool latency_mode = h->cfg.streams == 1 && h->cfg.max_batch <= 16;
-    const unsigned mask = (unsigned)env_int("RF_TILE_MASK", (int)(latency_mode ? TM_LATENCY : TM_THROUGHPUT));
+    const unsigned dflt = !latency_mode ? TM_THROUGHPUT : (h->cfg.max_batch <= 2 ? TM_LATENCY_SMALL : TM_LATENCY);
+    const unsigned mask = (unsigned)env_int("RF_TILE_MASK", (int)dflt);
     for (unsigned m : {mask, mask & ~(unsigned)(TM_HEAD | TM_NMS)}) {
         // a failed attempt leaves no trace
         h->steps.clear(); h->tensors.clear(); h->tensor_by_name.clear(); h->chains.clear();
