@@ -155,6 +155,11 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsr
     const unsigned sz = valid ? 16u : 0u;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
 }
+// same with the destination given as a shared-window address (tc::smem_u32 hoisted out of the caller's loop)
+__device__ __forceinline__ void cp_async16_zfill_s(uint32_t smem_dst, const void *gsrc, bool valid) {
+    const unsigned sz = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
@@ -499,10 +504,14 @@ __global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(con
     __syncthreads();
     pdl_wait();
     const int lg = 31 - __clz(G);        // C / 8 is a power of two
-    for (int it = tid; it < R * G; it += TC_THREADS) {
-        const int g = it & (G - 1), pl = it >> lg;
-        const int off = s_off[pl];
-        cp_async16_zfill(sS + (size_t)it * 16, a.in + (off >= 0 ? off + g * 8 : 0), off >= 0);
+    {
+        // TC_THREADS is a multiple of G: a thread keeps its channel group; item `it` lands at sS + it * 16
+        const uint32_t sS_s = tc::smem_u32(sS);
+        const __half *src_g = a.in + (tid & (G - 1)) * 8;
+        for (int it = tid; it < R * G; it += TC_THREADS) {
+            const int off = s_off[it >> lg];
+            cp_async16_zfill_s(sS_s + (uint32_t)it * 16u, off >= 0 ? src_g + off : a.in, off >= 0);
+        }
     }
     cp_async_wait_all();
     __syncthreads();

@@ -92,15 +92,17 @@ __global__ void __launch_bounds__(TC_THREADS, 4) k_tc_dwpw_2d(const TcDw2dArgs a
         // item i of a row = (column px = i / G, group g = i % G): with C = 8 G its source is src_row + 8 i halfs -- affine in i
         const int per_row = PW << lg;
         const int px_lo = max(0, -ix0), px_hi = min(PW, a.IW - ix0);       // columns inside the map
+        const unsigned px_n = (unsigned)max(px_hi - px_lo, 0);
+        const uint32_t sS_s = tc::smem_u32(sS);
         for (int py = warp; py < PH; py += TC_THREADS / 32) {
             const int iy = iy0 + py;
             const bool rowok = iy >= 0 && iy < a.IH;
             const __half *src_row = a.in + (ptrdiff_t)(((b * a.IH + (rowok ? iy : 0)) * a.IW + ix0) * a.C);
-            unsigned char *dst_row = sS + py * PW * pix;
+            const uint32_t dst_row = sS_s + (uint32_t)(py * PW * pix);
+            const __half *zsrc = a.in;      // any valid address: zero bytes are read from it
             for (int i = lane; i < per_row; i += 32) {
-                const int px = i >> lg;
-                const bool ok = rowok && px >= px_lo && px < px_hi;
-                cp_async16_zfill(dst_row + i * 16, src_row + (ok ? i * 8 : -ix0 * a.C), ok);
+                const bool ok = rowok && (unsigned)((i >> lg) - px_lo) < px_n;
+                cp_async16_zfill_s(dst_row + (uint32_t)i * 16u, ok ? src_row + i * 8 : zsrc, ok);
             }
         }
     }
