@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 ( time python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/final_smoke.log 2>&1
 ( time python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_r02_final_1gpu.json 2> gpurun_out/bench_r02_final_1gpu.err ) > gpurun_out/final_bench_time.log 2>&1
 ( time python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_r02_final_ref.json 2> gpurun_out/bench_r02_final_ref.err ) > gpurun_out/final_ref_time.log 2>&1
-python tools/mask_sweep.py --masks 9999,482,448,511 --batches 8,32 --streams 1,4,6 > gpurun_out/mask_sweep_final.log 2>&1
+python tools/mask_sweep.py --masks 9999,448,480,482,511 --batches 1,8,32 --streams 1,6 > gpurun_out/mask_sweep_final.log 2>&1
 tail -4 gpurun_out/final_pytest.log; tail -4 gpurun_out/final_smoke.log; tail -4 gpurun_out/final_bench_time.log; tail -4 gpurun_out/final_ref_time.log
 python - <<'PY'
 import json
