@@ -6,7 +6,7 @@
 // IPC; the CTA that finishes an image's NMS (postproc_dev.cuh nms_image -- the stand-alone k_nms or the last-block NMS of
 // the tile chains) stores the kept records straight into the window of EVERY rank over NVLink / NVSwitch peer mappings and
 // then raises that image's flag there.  No collective kernel, no extra launch on the producing side; a consumer orders its
-// reads behind one tiny kernel that waits for the step's flags (k_comm_wait).
+// reads behind one tiny kernel that waits for the step's flags (k_comm_wait_p, the last node of the forward graph).
 //
 // Window of one rank: [ring][world][max_batch] x {max_faces records, count, flag}.  A step with sequence number q uses slot
 // q % ring of every window.  Flow control needs no acknowledgements: a rank can only run RF_PIPELINE_DEPTH + `streams`
@@ -35,13 +35,19 @@ static_assert(sizeof(CommBlob) == RF_COMM_BLOB_BYTES, "blob layout");
 size_t dets_bytes(rf_handle h, int world) { return sizeof(rf_det) * (size_t)COMM_RING * world * h->cfg.max_batch * h->cfg.max_faces; }
 size_t words(rf_handle h, int world) { return (size_t)COMM_RING * world * h->cfg.max_batch; }
 
-__global__ void __launch_bounds__(1024) k_comm_wait(const unsigned *flags, size_t base, int world, int max_batch, int n, unsigned seq, unsigned *err) {
+// The consumer side: one tiny kernel that waits for the step's flags of every rank, as the LAST NODE of the forward graph.
+// Sequence number and slot come from the run parameters in device memory (0 = this run has no exchange: return at once), so
+// one captured graph serves every step; a peer that never delivers is reported (err), not waited for forever
+__global__ void __launch_bounds__(1024) k_comm_wait_p(const unsigned *flags, const PostParams *__restrict__ params, int world, int max_batch, int n, unsigned *err) {
+    const unsigned seq = params->comm_seq;
+    if (!seq) return;
+    const size_t base = (size_t)params->comm_slot * world * max_batch;
     for (int t = threadIdx.x; t < world * n; t += blockDim.x) {
         const int r = t / n, i = t - r * n;
         const volatile unsigned *f = flags + base + (size_t)r * max_batch + i;
         unsigned spins = 0;
         while (*f != seq) {
-            if (++spins > (1u << 25)) { atomicMax(err, 1u + (unsigned)r); break; }   // a peer never delivered: report, do not hang
+            if (++spins > (1u << 25)) { atomicMax(err, 1u + (unsigned)r); break; }
             __nanosleep(200);
         }
     }
@@ -61,13 +67,12 @@ void comm_release(rf_handle h) {
     c = Comm{};
 }
 
-// Orders `s` behind the arrival of every rank's records of step (seq, slot).
-void comm_wait(rf_handle h, unsigned seq, unsigned slot, int n, cudaStream_t s) {
+// Orders `s` behind the arrival of every rank's records of the step the run parameters name.
+void comm_wait_in_graph(rf_handle h, int n, cudaStream_t s) {
     Comm &c = h->comm;
-    const size_t base = (size_t)slot * c.world * h->cfg.max_batch;
     const unsigned *flags = reinterpret_cast<const unsigned *>(c.window + dets_bytes(h, c.world) + words(h, c.world) * 4);
     const int threads = std::min(1024, std::max(32, c.world * n));
-    k_comm_wait<<<1, threads, 0, s>>>(flags, base, c.world, h->cfg.max_batch, n, seq, c.d_err);
+    k_comm_wait_p<<<1, threads, 0, s>>>(flags, h->d_params, c.world, h->cfg.max_batch, n, c.d_err);
     CK(cudaGetLastError());
 }
 

@@ -109,6 +109,9 @@ void run_steps(rf_handle h, int n, cudaStream_t s, bool use_lanes = true) {
     if (use_lanes)
         for (int l = 1; l < 3; l++)
             if (h->lane_last[l] >= 0) CK(cudaStreamWaitEvent(s, h->step_event[h->lane_last[l]], 0));
+    // multi-GPU handles: the wait for every rank's records of this step is the forward's last node (a no-op kernel for runs
+    // without an exchange), not a separate launch behind the graph
+    if (h->comm.ready && !h->profiling) comm_wait_in_graph(h, n, s);
 }
 
 void forward_graph(rf_handle h, int n) {
@@ -459,7 +462,6 @@ static int detect_device_impl(rf_handle h, const uint8_t *dev_bgr, int n, float 
         if (n > 0) forward_graph(h, n);
         if (gather) {
             const unsigned slot = seq % (unsigned)h->comm.ring;
-            comm_wait(h, seq, slot, n, h->stream);
             const size_t img0 = (size_t)slot * h->comm.world * h->cfg.max_batch;
             if (dev_dets) *dev_dets = h->pb.comm.dets[h->comm.rank] + img0 * h->cfg.max_faces;
             if (dev_counts) *dev_counts = h->pb.comm.counts[h->comm.rank] + img0;
@@ -730,7 +732,6 @@ static int submit_impl(rf_handle h, const uint8_t *const *imgs, int n, float thr
                 CK(cudaHostAlloc(&cs.h_counts, sizeof(int) * nimg, cudaHostAllocDefault));
             }
             const unsigned slot = seq % (unsigned)h->comm.ring;
-            comm_wait(h, seq, slot, n, h->stream);
             const size_t img0 = (size_t)slot * nimg;
             CK(cudaMemcpyAsync(cs.h_counts, h->pb.comm.counts[h->comm.rank] + img0, sizeof(int) * nimg, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaMemcpyAsync(cs.h_dets, h->pb.comm.dets[h->comm.rank] + img0 * h->cfg.max_faces, sizeof(rf_det) * nimg * h->cfg.max_faces, cudaMemcpyDeviceToHost,

@@ -277,7 +277,7 @@ cudaError_t tile_init();
 std::string describe_chains(rf_handle h);
 // ---- exported by comm.cu --------------------------------------------------------------------------------------------
 void comm_release(rf_handle h);
-void comm_wait(rf_handle h, unsigned seq, unsigned slot, int n, cudaStream_t s);
+void comm_wait_in_graph(rf_handle h, int n, cudaStream_t s);   // last node of the forward once a communicator exists
 // ---- exported by jpeg.cu (f1 ingest: nvJPEG decode into device memory) ------------------------------------------------
 int jpeg_info(rf_handle h, const uint8_t *data, size_t len, int *w, int *hgt);
 int jpeg_decode(rf_handle h, const uint8_t *const *data, const size_t *len, int n, uint8_t *const *dst, const int *w, const int *hgt, cudaStream_t s);

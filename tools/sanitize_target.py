@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Short end-to-end scenario for compute-sanitizer (memcheck): throughput plan, chain plan, INT8, letter-box (both resize
-definitions), fused exchange between two handles, views.  compute-sanitizer --tool memcheck python tools/sanitize_target.py"""
+definitions).  (The fused exchange needs one process per rank: tests/comm_worker.py, tools/comm_check.py.)  compute-sanitizer --tool memcheck python tools/sanitize_target.py"""
 import os
 import sys
 
@@ -36,18 +36,6 @@ def main():
     eng = Engine(cm2, 448, 448, precision=RF_PREC_INT8, max_batch=3, int8_table=os.path.join(GOLD, "weights", "mnet-deconv-0517.table.int8"))
     print("int8", [len(x) for x in eng.detect_batch(batch, 0.9, 0.4)])
     eng.close()
-    # fused exchange, two handles in one process
-    a = Engine(cm, 448, 448, precision=RF_PREC_FP16, max_batch=2, max_faces=64)
-    b = Engine(cm, 448, 448, precision=RF_PREC_FP16, max_batch=2, max_faces=64)
-    blobs = [a.comm_export(0, 2), b.comm_export(1, 2)]
-    a.comm_init(blobs)
-    b.comm_init(blobs)
-    ta = a.submit(batch[:2], 0.9, 0.4, allgather=True)
-    tb = b.submit(batch[1:3], 0.9, 0.4, allgather=True)
-    ra, rb = a.collect(ta), b.collect(tb)
-    print("exchange", type(ra).__name__, type(rb).__name__)
-    a.close()
-    b.close()
 
 
 if __name__ == "__main__":
