@@ -424,7 +424,7 @@ inline size_t tc_dw_smem_bytes(const TcDwArgs &a) {
 // (small C, thousands of CTAs: registers are better spent on occupancy; all lanes of a warp read the same
 // few addresses, so the shared reads are broadcasts).
 template <int NT, bool WREG>
-__global__ void __launch_bounds__(TC_THREADS, WREG ? 2 : 4) k_tc_dwpw_staged(const TcDwArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, WREG ? 3 : 4) k_tc_dwpw_staged(const TcDwArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar_b, bar_done;
     __shared__ uint32_t s_tmem;
