@@ -482,7 +482,7 @@ def main():
         line = dict(metric="faces/sec (end-to-end detect)", value=main_res["value"], unit="faces/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=main_res["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype={RF_PREC_FP16: "f16", RF_PREC_FP32: "f32", RF_PREC_INT8: "s8"}[prec], data="synthetic",
-                    config=dict(config, execution_contexts=args.streams or 6,
+                    config=dict(config, execution_contexts=args.streams or 8,
                                 l2_policy=f"input ring of {ring} batches = {ring * img_bytes / 2**20:.0f} MiB > 2x L2; activations reused in place",
                                 timing=f"median over {main_res['timed_blocks']} blocks of {K} steps ({main_res['timed_region_s']:.2f} s timed)",
                                 exchange=("detection records of every step stored into every rank's gather window by the NMS kernel (NVLink peer "

@@ -74,7 +74,7 @@ typedef struct rf_config {
     int max_image_w, max_image_h;  /* largest caller image (reference: 4096x3072, RetinaFace.cpp:325); 0 -> net size */
     unsigned flags;                /* RF_FLAG_* */
     int streams;                   /* execution contexts the asynchronous entry points rotate through so that
-                                      consecutive batches overlap on the GPU; 0 -> 6, max RF_MAX_STREAMS.  The blocking
+                                      consecutive batches overlap on the GPU; 0 -> RF_MAX_STREAMS (8).  The blocking
                                       rf_detect_batch always uses context 0.  1 selects the latency-oriented layer plan. */
     const char *prototxt_path;     /* optional: the Caffe prototxt of the model (buildTrtContext's first argument, RetinaFace.cpp:276).
                                       Parsed as protobuf text, checked to be the RetinaFace mnet25 graph, and its per-layer

@@ -352,7 +352,7 @@ int rf_create(const rf_config *cfg, rf_handle *out) {
         memset(h->tile_dbg, 0, 64);
         CK(cudaHostGetDevicePointer(&h->tile_dbg_dev, h->tile_dbg, 0));
         // ---- per-context resources ----
-        h->nctx = h->cfg.streams <= 0 ? 6 : std::min(h->cfg.streams, RF_MAX_STREAMS);
+        h->nctx = h->cfg.streams <= 0 ? RF_MAX_STREAMS : std::min(h->cfg.streams, RF_MAX_STREAMS);
         h->saved.resize(h->nctx);
         for (int c = 0; c < h->nctx; c++) {
             switch_ctx(h, c);

@@ -366,7 +366,7 @@ def test_cpp_driver_on_golden_photo(golden_image, tmp_path):
 
 def test_pipelined_submit_collect_equals_blocking(golden_image):
     """rf_submit_batch / rf_collect_batch (H2D of batch i+1 overlapping the kernels of batch i) returns exactly
-    what the blocking rf_detect_batch returns, RF_PIPELINE_DEPTH batches in flight over the default 6 execution contexts."""
+    what the blocking rf_detect_batch returns, RF_PIPELINE_DEPTH batches in flight over the default 8 execution contexts."""
     from retinaface_b200 import RF_PREC_FP16, RfError
     from retinaface_b200.capi import PIPELINE_DEPTH
     inp = letterbox_bgr_u8(golden_image, 448, 448)
