@@ -701,7 +701,7 @@ static bool build_tiles_with_mask(rf_handle h, unsigned mask) {
 
 void build_plan_tiles(rf_handle h) {
     // the chain plan pays off for one forward at a time AND small batches (profiles/r02_mask_sweep.txt: one context, batch 1:
-    // 107.7 us against 113.6 us per-layer; batch 8: 165.2 against 165.7 us; batch 32: 456 against 420 us -- there every kernel
+    // 111.5 us against 116.7 us per-layer; batch 8: 162.8 against 163.6 us; batch 32: 420 against 387 us -- there every kernel
     // fills the GPU)
     const bool latency_mode = h->cfg.streams == 1 && h->cfg.max_batch <= 16;
     const unsigned dflt = !latency_mode ? TM_THROUGHPUT : (h->cfg.max_batch <= 2 ? TM_LATENCY_SMALL : TM_LATENCY);
