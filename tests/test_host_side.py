@@ -203,3 +203,19 @@ def test_tile_plan_of_the_headline_config(built_lib, monkeypatch):
     assert int(thr.split()[0]) == 29 and "heads_1x1+softmax+decode+nms_all_levels" in thr and "sort+nms" not in thr
     legacy = plan_describe(caffemodel("mnet25"), 448, 448, max_batch=8, flags=RF_FLAG_LEGACY_TC)
     assert int(legacy.split()[0]) == 29 and "tile_" not in legacy
+
+
+def test_fast_div_multiplier_is_exact_over_the_kernels_ranges():
+    """csrc/common.cuh fast_div: q = umulhi(n, ceil(2^32 / d)) replaces the run-time integer divisions of the tile / pixel index
+    math.  It is exact while n * d < 2^32; the kernels divide block indices (< 2^20), padded row numbers and GEMM row numbers
+    by map widths / heights / tile counts (<= a few thousand).  Restated here and checked against // over those ranges."""
+    import numpy as np
+    for d in [1, 2, 3, 7, 8, 14, 15, 16, 28, 29, 30, 40, 56, 57, 58, 98, 112, 114, 196, 224, 226, 449, 784, 897, 1282, 2240, 3136]:
+        mul = 0 if d <= 1 else ((1 << 32) + d - 1) // d
+        n = np.arange(0, min(1 << 21, (1 << 32) // d), dtype=np.uint64)
+        q = n if mul == 0 else (n * np.uint64(mul)) >> np.uint64(32)
+        assert np.array_equal(q, n // np.uint64(d)), d
+        # floor division of negative numerators (first tile: lo = -Wp): -fast_div(-n + d - 1)
+        neg = np.arange(1, 4 * d + 1, dtype=np.int64)
+        qq = -(((neg + d - 1).astype(np.uint64) * np.uint64(mul)) >> np.uint64(32)).astype(np.int64) if mul else -neg
+        assert np.array_equal(qq, -((neg + d - 1) // d)) and np.array_equal(qq, np.floor_divide(-neg, d)), d
