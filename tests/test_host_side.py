@@ -219,3 +219,26 @@ def test_fast_div_multiplier_is_exact_over_the_kernels_ranges():
         neg = np.arange(1, 4 * d + 1, dtype=np.int64)
         qq = -(((neg + d - 1).astype(np.uint64) * np.uint64(mul)) >> np.uint64(32)).astype(np.int64) if mul else -neg
         assert np.array_equal(qq, -((neg + d - 1) // d)) and np.array_equal(qq, np.floor_divide(-neg, d)), d
+
+
+def test_header_is_plain_c_and_links(built_lib, tmp_path):
+    """include/rf_b200.h is the drop-in boundary for ANY FFI: it must compile as C99 (no C++, no CUDA, no torch types) and a C
+    program must link against the library and run the calls that need no GPU."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "rf_b200.h"\n'
+                   'int main(void) {\n'
+                   '    rf_config c; memset(&c, 0, sizeof c);\n'
+                   '    int fmc = 0; int strides[8]; float anchors[64];\n'
+                   '    if (rf_abi_version() != 2) return 1;\n'
+                   '    if (rf_create(NULL, NULL) >= 0) return 2;                 /* argument errors are status codes, not aborts */\n'
+                   '    printf("%s | %s\\n", rf_build_info(), rf_status_string(RF_ERR_INVALID_ARG));\n'
+                   '    (void)c; (void)fmc; (void)strides; (void)anchors;\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(built_lib)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lrf_b200", f"-Wl,-rpath,{libdir}"])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sm_100a" in r.stdout
